@@ -1,0 +1,133 @@
+/* spb200 -- C ABI of the B200-native SuperPoint homography-adaptation / extraction hot path.
+ *
+ * One shared library (libspb200.so, sm_100a only).  Every entry point is `extern "C"`, takes plain
+ * pointers and sizes (no torch types), returns 0 on success or a negative SPB_E* code and never
+ * throws; `spb_last_error_string()` describes the last failure on the calling thread.
+ *
+ * Conventions
+ *   - every data pointer is a DEVICE pointer unless the comment says HOST;
+ *   - `stream` is a `cudaStream_t` passed as `void*` (0 = legacy default stream); kernels are only
+ *     enqueued, never synchronised; nothing is allocated after `spb_net_create`;
+ *   - images are row-major fp32 [H,W]; homographies are row-major fp32 [N,3,3] acting on the
+ *     reference's normalised coordinates (u,v in [-1,1], `torch.linspace(-1,1,W)` per pixel);
+ *   - the caller owns every buffer, including workspaces (sizes from the *_workspace_bytes calls).
+ *
+ * Each declaration cites the reference interface (file:line under eric-yyjau/pytorch-superpoint)
+ * that it replaces.  INTEGRATION.md shows the reference-side ctypes binding.
+ */
+#ifndef SPB200_H
+#define SPB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPB_OK 0
+#define SPB_EINVAL (-1)   /* bad argument (null pointer, unsupported size) */
+#define SPB_ECUDA (-2)    /* a CUDA runtime/driver call failed              */
+#define SPB_ENOMEM (-3)   /* workspace too small / allocation failed        */
+#define SPB_EARCH (-4)    /* device is not sm_100                           */
+
+#define SPB_MODE_BILINEAR 0
+#define SPB_MODE_NEAREST 1
+
+#define SPB_IMPL_TCGEN05 0 /* bf16 implicit-GEMM on tcgen05/TMEM fed by TMA (product path)        */
+#define SPB_IMPL_SIMT 1    /* CUDA-core bring-up/validation kernels with the same bf16 numerics  */
+
+int spb_version(void);
+const char* spb_last_error_string(void);
+
+/* ---- (1) homography warp ------------------------------------------------------------------------
+ * utils/utils.py:318-351 `inv_warp_image_batch(img, mat_homo_inv, device, mode)` incl. warp_points
+ * (286-314) and F.grid_sample(align_corners=True, zero padding).
+ *   out[n](p) = img[n](M[n].p).  img_batch_stride = elements between consecutive source images;
+ *   0 broadcasts ONE image to all N warps (the HA case `img.repeat(N,1,1,1)`, datasets/Coco.py:279,
+ *   never materialised). */
+int spb_inv_warp_image_batch(const float* img, long long img_batch_stride, const float* mats, float* out,
+                             int N, int H, int W, int mode, void* stream);
+
+/* utils/utils.py:677-704 `compute_valid_mask(image_shape, inv_homography, device, erosion_radius=0)`:
+ * nearest-mode warp of an all-ones image -> mask[N,H,W] in {0,1} (fp32, like the reference). */
+int spb_compute_valid_mask(const float* mats, float* mask, int N, int H, int W, void* stream);
+
+/* ---- (3) heat-map ---------------------------------------------------------------------------------
+ * utils/utils.py:480-525 `flattenDetection(semi, tensor=True)` + utils/d2s.py:8-25 DepthToSpace(8):
+ * softmax over 65 channels, drop the dustbin, pixel-shuffle.  semi is NCHW fp32 [B,65,Hc,Wc]
+ * (the reference layout) when nhwc_cstride == 0, else NHWC with that channel stride (>= 65).
+ * heat is [B,8Hc,8Wc]. */
+int spb_flatten_detection(const float* semi, int nhwc_cstride, float* heat, int B, int Hc, int Wc, void* stream);
+
+/* export.py:49-63 `combine_heatmap(heatmap, inv_homographies, mask_2D, device)` on materialised
+ * heat/mask [N,H,W]: out[H,W] = sum_n unwarp_n(heat_n*mask_n) / sum_n unwarp_n(mask_n). */
+int spb_combine_heatmap(const float* heat, const float* mask, const float* mats_unwarp, float* out,
+                        int N, int H, int W, void* stream);
+
+/* The fused form of utils.py:480-525 + utils.py:677-704 + export.py:49-62 used by the HA path:
+ * semi (NHWC fp32, channel stride cstride) of N warped views -> per-cell softmax, dustbin drop,
+ * depth-to-space, analytic valid mask (from mats_fwd), bilinear un-warp (mats_unwarp) and the two
+ * sums over the N views.  sums[2,H,W] = {sum heat*mask, sum mask}; accumulate != 0 adds to the
+ * existing content (used when the homographies of one image arrive in several chunks).
+ * ws must hold spb_ha_aggregate_workspace_bytes(N,H,W). */
+size_t spb_ha_aggregate_workspace_bytes(int N, int H, int W);
+int spb_ha_aggregate(const float* semi_nhwc, int cstride, const float* mats_unwarp, const float* mats_fwd,
+                     int N, int H, int W, float* sums, int accumulate, void* ws, size_t ws_bytes, void* stream);
+/* export.py:63 the final division (after the NCCL all-reduce of `sums` when N is sharded). */
+int spb_ha_finalize(const float* sums, float* heat, int H, int W, void* stream);
+
+/* ---- (4) threshold + greedy grid NMS + border removal + top-k -----------------------------------
+ * models/model_wrap.py:252-279 `getPtsFromHeatmap` incl. `nms_fast` (117-180) and export.py:322-328
+ * (`pts[:top_k]`).  heat [B,H,W].  For image b, pts[b, j, :] = (x, y, conf) for j < counts[b],
+ * ordered like the reference (confidence descending; ties: larger row-major index first), cut to
+ * min(top_k, capacity) rows (top_k <= 0: no cut).  Exact: identical index sets and order to the
+ * reference run with a stable argsort.  total[b] (may be NULL) receives the un-cut survivor count. */
+size_t spb_nms_workspace_bytes(int B, int H, int W, int nms_dist);
+int spb_get_pts_from_heatmap(const float* heat, int B, int H, int W, float conf_thresh, int nms_dist,
+                             int border_remove, int top_k, int capacity, float* pts, int* counts, int* total,
+                             void* ws, size_t ws_bytes, void* stream);
+
+/* ---- (5) descriptor sampling -----------------------------------------------------------------------
+ * models/model_wrap.py:281-299 `sample_desc_from_points(coarse_desc, pts)`: bilinear
+ * grid_sample(align_corners=True) of the coarse descriptor map at x*(Wc-1)/W-style coordinates
+ * (the reference's normalisation quirk is kept), then L2 normalisation.
+ *   coarse: fp32, NCHW [D,Hc,Wc] when nhwc == 0 (reference layout) or NHWC [Hc,Wc,D] when nhwc != 0.
+ *   pts: [K,3] rows (x, y, conf) as produced by spb_get_pts_from_heatmap; count: DEVICE int* with the
+ *   number of valid rows (NULL: all K rows).  out: [K,D] (row k = descriptor of point k). */
+int spb_sample_desc_from_points(const float* coarse, int nhwc, const float* pts, const int* count, int K,
+                                int Hc, int Wc, int D, int cell, float* out, void* stream);
+
+/* ---- (2) network ------------------------------------------------------------------------------------
+ * models/SuperPointNet_pretrained.py:46-76, SuperPointNet_gauss2.py:43-70, SuperPointNet.py:154-224.
+ * weights/biases: HOST pointers, 12 layers in the order conv1a,1b,2a,2b,3a,3b,4a,4b,Pa,Pb,Da,Db;
+ * weights fp32 OIHW with eval-mode BatchNorm already folded in (w*g/sqrt(v+eps)), biases likewise. */
+typedef struct spb_net spb_net;
+int spb_net_create(spb_net** net, const float* const* weights, const float* const* biases);
+int spb_net_destroy(spb_net* net);
+int spb_net_set_impl(spb_net* net, int impl); /* SPB_IMPL_* (default TCGEN05) */
+/* views processed per pass by spb_ha_heatmap_sums (0 = all N at once); bounds the workspace and lets
+ * the inter-layer activations of a pass stay L2-resident */
+int spb_net_set_ha_chunk(spb_net* net, int views);
+size_t spb_net_workspace_bytes(int B, int H, int W, int want_desc);
+/* x [B,1,H,W] fp32 (H, W multiples of 8) -> semi NHWC fp32 [B,H/8,W/8,65];
+ * desc NHWC fp32 [B,H/8,W/8,256], L2-normalised over channels (NULL: detector head only). */
+int spb_net_forward(spb_net* net, const float* x, int B, int H, int W, float* semi, float* desc,
+                    void* ws, size_t ws_bytes, void* stream);
+/* Debug/validation: run ONE layer (index 0..11) on NHWC bf16 input (fp32 [B,H,W] for layer 0);
+ * output NHWC bf16 (fp32 for Pb/Db), 2x2 max-pool applied where the network has one. */
+int spb_net_layer(spb_net* net, int layer, const void* in, void* out, int B, int H, int W, void* stream);
+
+/* ---- the whole HA step for one image (datasets/Coco.py:262-284 + export.py:309-310) -------------
+ * img [H,W] fp32; mats_fwd = sample['inv_homographies'] (warps the image, defines the valid mask),
+ * mats_unwarp = sample['homographies'] (un-warps the heat-map); both [N,3,3] for the N views THIS
+ * caller owns (all of them on one GPU, a shard under homography sharding).
+ * Does: warp N views -> detector network -> fused aggregate into sums[2,H,W]. */
+size_t spb_ha_workspace_bytes(int N, int H, int W);
+int spb_ha_heatmap_sums(spb_net* net, const float* img, const float* mats_unwarp, const float* mats_fwd,
+                        int N, int H, int W, float* sums, int accumulate, void* ws, size_t ws_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPB200_H */

@@ -1,0 +1,13 @@
+"""pytorch_superpoint_b200 -- B200-native (sm_100a) SuperPoint homography-adaptation / extraction hot path.
+
+Host-side mirror of the reference's interface for this path (``utils/utils.py``, ``export.py``,
+``models/model_wrap.py``, ``models/SuperPointNet*.py`` of eric-yyjau/pytorch-superpoint) over the C ABI
+of ``libspb200.so`` (``include/spb200.h``).  Importing the package needs neither a GPU nor the built
+library; calling any operator does, and raises otherwise -- there is no CPU fallback.
+"""
+from .homographies import EXPORT_PARAMS, make_ha_homographies, sample_homography  # noqa: F401
+from .net import SuperPointNet_b200, fold_state_dict  # noqa: F401
+from .ops import (combine_heatmap, compute_valid_mask, flattenDetection, getPtsFromHeatmap,  # noqa: F401
+                  inv_warp_image_batch, sample_desc_from_points)
+
+__version__ = "0.1.0"

@@ -1,0 +1,72 @@
+"""ctypes binding of libspb200.so (the C ABI declared in include/spb200.h).
+
+There is no CPU fallback: ``lib()`` raises if the library is missing or cannot be loaded, and
+``check()`` turns every non-zero return code into a ``RuntimeError`` carrying
+``spb_last_error_string()``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libspb200.so")
+
+_p = C.c_void_p
+_i = C.c_int
+_f = C.c_float
+_z = C.c_size_t
+_ll = C.c_longlong
+
+# name -> (restype, argtypes); mirrors include/spb200.h one to one
+PROTOTYPES = {
+    "spb_version": (_i, []),
+    "spb_last_error_string": (C.c_char_p, []),
+    "spb_inv_warp_image_batch": (_i, [_p, _ll, _p, _p, _i, _i, _i, _i, _p]),
+    "spb_compute_valid_mask": (_i, [_p, _p, _i, _i, _i, _p]),
+    "spb_flatten_detection": (_i, [_p, _i, _p, _i, _i, _i, _p]),
+    "spb_combine_heatmap": (_i, [_p, _p, _p, _p, _i, _i, _i, _p]),
+    "spb_ha_aggregate_workspace_bytes": (_z, [_i, _i, _i]),
+    "spb_ha_aggregate": (_i, [_p, _i, _p, _p, _i, _i, _i, _p, _i, _p, _z, _p]),
+    "spb_ha_finalize": (_i, [_p, _p, _i, _i, _p]),
+    "spb_nms_workspace_bytes": (_z, [_i, _i, _i, _i]),
+    "spb_get_pts_from_heatmap": (_i, [_p, _i, _i, _i, _f, _i, _i, _i, _i, _p, _p, _p, _p, _z, _p]),
+    "spb_sample_desc_from_points": (_i, [_p, _i, _p, _p, _i, _i, _i, _i, _i, _p, _p]),
+    "spb_net_create": (_i, [C.POINTER(_p), C.POINTER(_p), C.POINTER(_p)]),
+    "spb_net_destroy": (_i, [_p]),
+    "spb_net_set_impl": (_i, [_p, _i]),
+    "spb_net_set_ha_chunk": (_i, [_p, _i]),
+    "spb_net_workspace_bytes": (_z, [_i, _i, _i, _i]),
+    "spb_net_forward": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _z, _p]),
+    "spb_net_layer": (_i, [_p, _i, _p, _p, _i, _i, _i, _p]),
+    "spb_ha_workspace_bytes": (_z, [_i, _i, _i]),
+    "spb_ha_heatmap_sums": (_i, [_p, _p, _p, _p, _i, _i, _i, _p, _i, _p, _z, _p]),
+}
+# debug knobs exported by the library but not part of the public header
+_EXTRA = {"spb_conv_tc_set_halo": (_i, [_i])}
+
+IMPL_TCGEN05, IMPL_SIMT = 0, 1
+MODE_BILINEAR, MODE_NEAREST = 0, 1
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m pytorch_superpoint_b200.build` "
+                "(nvcc, sm_100a).  There is no CPU fallback.")
+        h = C.CDLL(LIB_PATH)
+        for name, (res, args) in {**PROTOTYPES, **_EXTRA}.items():
+            fn = getattr(h, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = h
+    return _lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = lib().spb_last_error_string().decode(errors="replace")
+        raise RuntimeError(f"libspb200 {what} failed (rc={rc}): {msg}")

@@ -1,0 +1,490 @@
+// (2) bf16 implicit-GEMM convolution on tcgen05 / TMEM fed by TMA  (sm_100a).
+// Replaces the nn.Conv2d(+BatchNorm2d eval, ReLU, MaxPool2d) chain of
+// models/SuperPointNet_pretrained.py:56-73, SuperPointNet_gauss2.py:53-63 / unet_parts.py:14-21,41-44.
+//
+// GEMM view per CTA tile:  D[128 pixels, Cout] = sum_{tap, cin-chunk} A_tap[128 px, 64] . W_tap[64, Cout]
+//   * activations are NHWC bf16, so one pixel's 64 channels are exactly one 128-byte SWIZZLE_128B row;
+//   * the output tile is 16 rows x 8 columns of pixels (M = 128); every 8-row UMMA core-matrix group
+//     is one image row, groups are SBO apart -- therefore the 9 filter taps are 9 *shifted views* of ONE
+//     halo block (18 x 10 pixels) that TMA loads once per (tile, 64-channel chunk): the A descriptor's
+//     start address moves by (r*10 + s)*128 B, SBO stays 10*128 B.  Out-of-image halo pixels are zero
+//     filled by TMA (negative / overflowing box coordinates) = the conv's zero padding;
+//   * weights are K-major rows [Cout][tap*Cin + ci]; small layers keep all 9 (x chunks) blocks
+//     resident in shared memory for the life of the persistent CTA, big ones stream them through a ring;
+//   * accumulators live in TMEM (double buffered), one elected thread issues tcgen05.mma, four
+//     epilogue warps read TMEM with tcgen05.ld and apply bias + ReLU + 2x2 max-pool (lane shuffles)
+//     + bf16 pack (or fp32 / channel-L2-normalised output for the two heads).
+// Warp roles: 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2..5 = epilogue.
+#include <cuda.h>
+
+#include "net.cuh"
+
+namespace spb {
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Bounded wait: a protocol bug must abort the kernel, not hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  const long long t0 = clock64();
+  while (true) {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (clock64() - t0 > 4000000000LL) {
+      printf("spb200 conv_tc: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x,
+             threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+// [0,14) start>>4, [16,30) LBO>>4 (unused for swizzled K-major), [32,46) SBO>>4, [46,48) version=1,
+// [61,64) layout (2 = SWIZZLE_128B).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)1 << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, M x N.
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------------
+// configuration
+// ------------------------------------------------------------------------------------------------
+template <int CIN_, int NPAD_, int KS_, bool HALO_, bool BRES_, int NA_, int NB_>
+struct ConvCfg {
+  static constexpr int CIN = CIN_, NPAD = NPAD_, KS = KS_, NA = NA_;
+  static constexpr bool HALO = HALO_ && KS_ > 1, BRES = BRES_;
+  static constexpr int TAPS = KS * KS, CHUNKS = CIN / 64;
+  static constexpr int TH = 16, TW = 8;
+  static constexpr int P = HALO ? TW + KS - 1 : TW;  // pixels per shared-memory row of an A block
+  static constexpr int R = HALO ? TH + KS - 1 : TH;
+  static constexpr int A_BYTES = P * R * 128;
+  static constexpr int A_STRIDE = (A_BYTES + 1023) / 1024 * 1024;
+  static constexpr int B_BYTES = NPAD * 128;
+  static constexpr int NBLK = TAPS * CHUNKS;
+  static constexpr int NBS = BRES ? NBLK : NB_;
+  static constexpr int ACC_STRIDE = NPAD <= 64 ? 64 : (NPAD <= 128 ? 128 : 256);
+  static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
+  static constexpr int NBAR = 2 * NA + 2 * NBS + 4;
+  static constexpr size_t SMEM = 1024 /*align slack*/ + (size_t)NA * A_STRIDE + (size_t)NBS * B_BYTES + NPAD * 4 +
+                                 NBAR * 8 + 16;
+  static_assert(B_BYTES % 1024 == 0, "weight block must keep 1024-byte alignment");
+  static_assert(SMEM <= 227 * 1024, "shared memory budget");
+};
+
+struct ConvArgs {
+  const float* bias;
+  void* out;
+  int B, H, W, cout;
+  int relu, pool, out_f32, l2norm;
+  int tiles_x, tiles_y, ntiles;
+};
+
+template <class C>
+__global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act,
+                                                         const __grid_constant__ CUtensorMap tm_wgt, ConvArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = sA + (size_t)C::NA * C::A_STRIDE;
+  float* sBias = reinterpret_cast<float*>(sB + (size_t)C::NBS * C::B_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + C::NPAD);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + C::NBAR);
+  const uint32_t bar0 = smem_u32(bars);
+  auto a_full = [&](int s) { return bar0 + 8u * s; };
+  auto a_empty = [&](int s) { return bar0 + 8u * (C::NA + s); };
+  auto b_full = [&](int s) { return bar0 + 8u * (2 * C::NA + s); };
+  auto b_empty = [&](int s) { return bar0 + 8u * (2 * C::NA + C::NBS + s); };
+  auto acc_full = [&](int s) { return bar0 + 8u * (2 * C::NA + 2 * C::NBS + s); };
+  auto acc_empty = [&](int s) { return bar0 + 8u * (2 * C::NA + 2 * C::NBS + 2 + s); };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  for (int i = threadIdx.x; i < C::NPAD; i += blockDim.x) sBias[i] = a.bias[i];
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::NA; ++s) {
+      mbar_init(a_full(s), 1);
+      mbar_init(a_empty(s), 1);
+    }
+    for (int s = 0; s < C::NBS; ++s) {
+      mbar_init(b_full(s), 1);
+      mbar_init(b_empty(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(acc_full(s), 1);
+      mbar_init(acc_empty(s), 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)C::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // =========================== TMA producer ===========================
+    if (lane == 0) {
+      int sa = 0, pa = 0, sb = 0, pb = 0;
+      bool first = true;
+      for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x) {
+        const int n = t / (a.tiles_x * a.tiles_y), rem = t % (a.tiles_x * a.tiles_y);
+        const int y0 = (rem / a.tiles_x) * C::TH, x0 = (rem % a.tiles_x) * C::TW;
+        for (int kc = 0; kc < C::CHUNKS; ++kc) {
+          if (C::HALO) {
+            mbar_wait(a_empty(sa), pa ^ 1);
+            mbar_expect_tx(a_full(sa), C::A_BYTES);
+            tma_load_4d(smem_u32(sA + (size_t)sa * C::A_STRIDE), &tm_act, a_full(sa), kc * 64, x0 - C::KS / 2,
+                        y0 - C::KS / 2, n);
+            if (++sa == C::NA) { sa = 0; pa ^= 1; }
+          }
+          for (int tap = 0; tap < C::TAPS; ++tap) {
+            if (!C::HALO) {
+              mbar_wait(a_empty(sa), pa ^ 1);
+              mbar_expect_tx(a_full(sa), C::A_BYTES);
+              tma_load_4d(smem_u32(sA + (size_t)sa * C::A_STRIDE), &tm_act, a_full(sa), kc * 64,
+                          x0 + tap % C::KS - C::KS / 2, y0 + tap / C::KS - C::KS / 2, n);
+              if (++sa == C::NA) { sa = 0; pa ^= 1; }
+            }
+            if (C::BRES) {
+              if (first) {
+                const int blk = kc * C::TAPS + tap;
+                mbar_expect_tx(b_full(blk), C::B_BYTES);
+                tma_load_2d(smem_u32(sB + (size_t)blk * C::B_BYTES), &tm_wgt, b_full(blk), tap * C::CIN + kc * 64, 0);
+              }
+            } else {
+              mbar_wait(b_empty(sb), pb ^ 1);
+              mbar_expect_tx(b_full(sb), C::B_BYTES);
+              tma_load_2d(smem_u32(sB + (size_t)sb * C::B_BYTES), &tm_wgt, b_full(sb), tap * C::CIN + kc * 64, 0);
+              if (++sb == C::NBS) { sb = 0; pb ^= 1; }
+            }
+          }
+        }
+        first = false;
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(128, C::NPAD);
+      int sa = 0, pa = 0, sb = 0, pb = 0, as = 0, pacc = 0;
+      for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x) {
+        mbar_wait(acc_empty(as), pacc ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)as * C::ACC_STRIDE;
+        uint32_t accumulate = 0;
+        for (int kc = 0; kc < C::CHUNKS; ++kc) {
+          if (C::HALO) mbar_wait(a_full(sa), pa);
+          for (int tap = 0; tap < C::TAPS; ++tap) {
+            if (!C::HALO) mbar_wait(a_full(sa), pa);
+            const int slot = C::BRES ? kc * C::TAPS + tap : sb;
+            mbar_wait(b_full(slot), C::BRES ? 0 : pb);
+            tc_fence_after();
+            uint32_t a_addr = smem_u32(sA + (size_t)sa * C::A_STRIDE);
+            if (C::HALO) a_addr += ((tap / C::KS) * C::P + (tap % C::KS)) * 128;
+            const uint32_t b_addr = smem_u32(sB + (size_t)slot * C::B_BYTES);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              tc_mma(d_tmem, make_desc(a_addr + k * 32, C::P * 128), make_desc(b_addr + k * 32, 1024), idesc,
+                     accumulate);
+              accumulate = 1;
+            }
+            if (!C::BRES) {
+              tc_commit(b_empty(sb));
+              if (++sb == C::NBS) { sb = 0; pb ^= 1; }
+            }
+            if (!C::HALO) {
+              tc_commit(a_empty(sa));
+              if (++sa == C::NA) { sa = 0; pa ^= 1; }
+            }
+          }
+          if (C::HALO) {
+            tc_commit(a_empty(sa));
+            if (++sa == C::NA) { sa = 0; pa ^= 1; }
+          }
+        }
+        tc_commit(acc_full(as));
+        if (++as == 2) { as = 0; pacc ^= 1; }
+      }
+    }
+  } else {
+    // =========================== epilogue (warps 2..5) ===========================
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may read
+    const int m = quad * 32 + lane, py = m >> 3, px = m & 7;
+    int as = 0, pacc = 0;
+    for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x) {
+      const int n = t / (a.tiles_x * a.tiles_y), rem = t % (a.tiles_x * a.tiles_y);
+      const int y = (rem / a.tiles_x) * C::TH + py, x = (rem % a.tiles_x) * C::TW + px;
+      mbar_wait(acc_full(as), pacc);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t)as * C::ACC_STRIDE + ((uint32_t)(quad * 32) << 16);
+      bool valid = y < a.H && x < a.W;
+      long long opix;
+      if (a.pool) {
+        valid = valid && !(px & 1) && !(py & 1);
+        opix = ((long long)n * (a.H >> 1) + (y >> 1)) * (a.W >> 1) + (x >> 1);
+      } else {
+        opix = ((long long)n * a.H + y) * a.W + x;
+      }
+      float inv_norm = 1.f;
+      if (a.l2norm) {
+        float ss = 0.f;
+        for (int c0 = 0; c0 < C::NPAD; c0 += 16) {
+          uint32_t v[16];
+          tc_ld16(taddr + c0, v);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float f = __uint_as_float(v[j]) + sBias[c0 + j];
+            ss = fmaf(f, f, ss);
+          }
+        }
+        inv_norm = sqrtf(ss);
+      }
+      for (int c0 = 0; c0 < C::NPAD; c0 += 16) {
+        uint32_t v[16];
+        tc_ld16(taddr + c0, v);
+        float f[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          f[j] = __uint_as_float(v[j]) + sBias[c0 + j];
+          if (a.relu) f[j] = fmaxf(f[j], 0.f);
+          if (a.pool) {
+            f[j] = fmaxf(f[j], __shfl_xor_sync(0xffffffffu, f[j], 1));
+            f[j] = fmaxf(f[j], __shfl_xor_sync(0xffffffffu, f[j], 8));
+          }
+          if (a.l2norm) f[j] = __fdiv_rn(f[j], inv_norm);
+        }
+        if (valid) {
+          if (a.out_f32) {
+            float* o = static_cast<float*>(a.out) + opix * a.cout + c0;
+            if (c0 + 16 <= a.cout && (a.cout & 3) == 0) {
+#pragma unroll
+              for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+            } else {
+              for (int j = 0; j < 16; ++j)
+                if (c0 + j < a.cout) o[j] = f[j];
+            }
+          } else {
+            __nv_bfloat16* o = static_cast<__nv_bfloat16*>(a.out) + opix * a.cout + c0;
+            uint32_t pk[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+              pk[j] = *reinterpret_cast<const uint32_t*>(&h);
+            }
+            *reinterpret_cast<uint4*>(o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            *reinterpret_cast<uint4*>(o + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty(as));
+      if (++as == 2) { as = 0; pacc ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+static int encode_weight_map(CUtensorMap* tm, const LayerDev& L) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_error("conv_tc: cuTensorMapEncodeTiled not available from the driver");
+    return SPB_ECUDA;
+  }
+  const cuuint64_t K = (cuuint64_t)L.ks * L.ks * L.cin;
+  cuuint64_t dims[2] = {K, (cuuint64_t)L.cout_pad};
+  cuuint64_t strides[1] = {K * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)L.cout_pad};
+  cuuint32_t es[2] = {1, 1};
+  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, L.w_tc, dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("conv_tc: cuTensorMapEncodeTiled(weights) failed with CUresult %d", (int)r);
+    return SPB_ECUDA;
+  }
+  return SPB_OK;
+}
+
+static int encode_act_map(CUtensorMap* tm, const void* in, int B, int H, int W, int C, int boxw, int boxh) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_error("conv_tc: cuTensorMapEncodeTiled not available from the driver");
+    return SPB_ECUDA;
+  }
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)boxw, (cuuint32_t)boxh, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(in), dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("conv_tc: cuTensorMapEncodeTiled(activations %dx%dx%dx%d box %dx%d) failed with CUresult %d", B, H, W, C,
+              boxw, boxh, (int)r);
+    return SPB_ECUDA;
+  }
+  return SPB_OK;
+}
+
+int conv_tc_prepare(LayerDev& L) {
+  L.tmap_w = malloc(sizeof(CUtensorMap) + 64);
+  if (!L.tmap_w) return SPB_ENOMEM;
+  CUtensorMap tm;
+  const int rc = encode_weight_map(&tm, L);
+  if (rc != SPB_OK) return rc;
+  memcpy(L.tmap_w, &tm, sizeof(tm));
+  return SPB_OK;
+}
+
+static int g_halo_mode = 1;  // 1: one halo block + shifted descriptors; 0: per-tap reload (debug/A-B)
+extern "C" int spb_conv_tc_set_halo(int on) {
+  g_halo_mode = on ? 1 : 0;
+  return SPB_OK;
+}
+
+template <class C>
+static int launch(const LayerDev& L, const __nv_bfloat16* in, void* out, int B, int H, int W, int out_f32, int l2norm,
+                  cudaStream_t st) {
+  CUtensorMap tm_act, tm_wgt;
+  memcpy(&tm_wgt, L.tmap_w, sizeof(tm_wgt));
+  int rc = encode_act_map(&tm_act, in, B, H, W, L.cin, C::P, C::R);
+  if (rc != SPB_OK) return rc;
+  ConvArgs a;
+  a.bias = L.bias;
+  a.out = out;
+  a.B = B;
+  a.H = H;
+  a.W = W;
+  a.cout = L.cout;
+  a.relu = L.relu;
+  a.pool = L.pool;
+  a.out_f32 = out_f32;
+  a.l2norm = l2norm;
+  a.tiles_x = ceil_div(W, C::TW);
+  a.tiles_y = ceil_div(H, C::TH);
+  a.ntiles = B * a.tiles_x * a.tiles_y;
+  SPB_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+  const int grid = a.ntiles < kNumSMs ? a.ntiles : kNumSMs;
+  conv_tc_kernel<C><<<grid, 192, C::SMEM, st>>>(tm_act, tm_wgt, a);
+  SPB_CHECK_LAUNCH();
+  return SPB_OK;
+}
+
+int conv_tc(const LayerDev& L, const __nv_bfloat16* in, void* out, int B, int H, int W, int out_f32, int l2norm,
+            cudaStream_t st) {
+  if (!L.tmap_w) {
+    set_error("conv_tc: layer has no weight tensor map");
+    return SPB_EINVAL;
+  }
+  if (L.pool && ((H | W) & 1)) {
+    set_error("conv_tc: pooled layer needs even H, W (got %dx%d)", H, W);
+    return SPB_EINVAL;
+  }
+  const bool halo = g_halo_mode != 0;
+  //                                   CIN NPAD KS HALO  BRES  NA NB
+  if (L.ks == 3 && L.cin == 64 && L.cout_pad == 64)
+    return halo ? launch<ConvCfg<64, 64, 3, true, true, 4, 0>>(L, in, out, B, H, W, out_f32, l2norm, st)
+                : launch<ConvCfg<64, 64, 3, false, true, 6, 0>>(L, in, out, B, H, W, out_f32, l2norm, st);
+  if (L.ks == 3 && L.cin == 64 && L.cout_pad == 128)
+    return halo ? launch<ConvCfg<64, 128, 3, true, true, 3, 0>>(L, in, out, B, H, W, out_f32, l2norm, st)
+                : launch<ConvCfg<64, 128, 3, false, true, 4, 0>>(L, in, out, B, H, W, out_f32, l2norm, st);
+  if (L.ks == 3 && L.cin == 128 && L.cout_pad == 128)
+    return halo ? launch<ConvCfg<128, 128, 3, true, false, 4, 6>>(L, in, out, B, H, W, out_f32, l2norm, st)
+                : launch<ConvCfg<128, 128, 3, false, false, 6, 6>>(L, in, out, B, H, W, out_f32, l2norm, st);
+  if (L.ks == 3 && L.cin == 128 && L.cout_pad == 256)
+    return halo ? launch<ConvCfg<128, 256, 3, true, false, 3, 4>>(L, in, out, B, H, W, out_f32, l2norm, st)
+                : launch<ConvCfg<128, 256, 3, false, false, 4, 4>>(L, in, out, B, H, W, out_f32, l2norm, st);
+  if (L.ks == 1 && L.cin == 256 && L.cout_pad == 80)
+    return launch<ConvCfg<256, 80, 1, false, true, 6, 0>>(L, in, out, B, H, W, out_f32, l2norm, st);
+  if (L.ks == 1 && L.cin == 256 && L.cout_pad == 256)
+    return launch<ConvCfg<256, 256, 1, false, true, 4, 0>>(L, in, out, B, H, W, out_f32, l2norm, st);
+  set_error("conv_tc: unsupported layer shape ks=%d cin=%d cout_pad=%d", L.ks, L.cin, L.cout_pad);
+  return SPB_EINVAL;
+}
+
+}  // namespace spb

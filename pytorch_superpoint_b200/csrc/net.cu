@@ -1,0 +1,240 @@
+// (2) SuperPointNet forward (encoder + detector/descriptor heads) and the whole-HA entry point.
+// models/SuperPointNet_pretrained.py:46-76, SuperPointNet_gauss2.py:43-70 (+unet_parts.py:10-48),
+// SuperPointNet.py:154-224 -- eval-mode BatchNorm is folded into the conv weights by the caller.
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "net.cuh"
+
+namespace spb {
+
+struct LayerSpec {
+  int cin, cout, ks, relu, pool;
+};
+static const LayerSpec kSpec[kNumLayers] = {
+    {1, 64, 3, 1, 0},    {64, 64, 3, 1, 1},    {64, 64, 3, 1, 0},   {64, 64, 3, 1, 1},
+    {64, 128, 3, 1, 0},  {128, 128, 3, 1, 1},  {128, 128, 3, 1, 0}, {128, 128, 3, 1, 0},
+    {128, 256, 3, 1, 0}, {256, 65, 1, 0, 0},   {128, 256, 3, 1, 0}, {256, 256, 1, 0, 0}};
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+static inline void* align_ptr(void* p) {  // workspaces carry 1 KB of slack for this
+  return reinterpret_cast<void*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~(uintptr_t)1023);
+}
+
+struct Workspace {  // carve-up of the caller's buffer for a batch of B views at H x W
+  __nv_bfloat16 *buf0, *buf1;
+  size_t bytes;
+  Workspace(void* base, int B, int H, int W) {
+    const size_t b0 = align_up((size_t)B * H * W * 64 * 2, 1024);
+    const size_t b1 = align_up((size_t)B * (H / 2) * (W / 2) * 64 * 2, 1024);
+    char* p = static_cast<char*>(base);
+    buf0 = reinterpret_cast<__nv_bfloat16*>(p);
+    buf1 = reinterpret_cast<__nv_bfloat16*>(p + b0);
+    bytes = b0 + b1;
+  }
+};
+
+static int run_layer(const Net* net, int li, const void* in, void* out, int B, int H, int W, int out_f32, int l2norm,
+                     cudaStream_t st) {
+  const LayerDev& L = net->layer[li];
+  if (li == 0) return conv1a_simt(L, static_cast<const float*>(in), static_cast<__nv_bfloat16*>(out), B, H, W, st);
+  if (net->impl == SPB_IMPL_TCGEN05)
+    return conv_tc(L, static_cast<const __nv_bfloat16*>(in), out, B, H, W, out_f32, l2norm, st);
+  int rc = conv_simt(L, static_cast<const __nv_bfloat16*>(in), out, B, H, W, out_f32, st);
+  if (rc == SPB_OK && l2norm) rc = l2norm_rows(static_cast<float*>(out), (long long)B * H * W, L.cout, st);
+  return rc;
+}
+
+static int forward(const Net* net, const float* x, int B, int H, int W, float* semi, float* desc, void* ws,
+                   cudaStream_t st) {
+  Workspace w(ws, B, H, W);
+  int rc;
+#define RUN(li, in, out, h, wd, f32, l2)                                     \
+  if ((rc = run_layer(net, li, in, out, B, h, wd, f32, l2, st)) != SPB_OK) return rc
+  RUN(0, x, w.buf0, H, W, 0, 0);
+  RUN(1, w.buf0, w.buf1, H, W, 0, 0);  // + pool -> H/2
+  RUN(2, w.buf1, w.buf0, H / 2, W / 2, 0, 0);
+  RUN(3, w.buf0, w.buf1, H / 2, W / 2, 0, 0);  // + pool -> H/4
+  RUN(4, w.buf1, w.buf0, H / 4, W / 4, 0, 0);
+  RUN(5, w.buf0, w.buf1, H / 4, W / 4, 0, 0);  // + pool -> H/8
+  RUN(6, w.buf1, w.buf0, H / 8, W / 8, 0, 0);
+  RUN(7, w.buf0, w.buf1, H / 8, W / 8, 0, 0);
+  RUN(8, w.buf1, w.buf0, H / 8, W / 8, 0, 0);
+  RUN(9, w.buf0, semi, H / 8, W / 8, 1, 0);
+  if (desc) {
+    RUN(10, w.buf1, w.buf0, H / 8, W / 8, 0, 0);
+    RUN(11, w.buf0, desc, H / 8, W / 8, 1, 1);
+  }
+#undef RUN
+  return SPB_OK;
+}
+
+}  // namespace spb
+
+using namespace spb;
+
+extern "C" {
+
+int spb_net_create(spb_net** out, const float* const* weights, const float* const* biases) {
+  SPB_CHECK_ARG(out && weights && biases);
+  int dev = 0;
+  cudaDeviceProp prop;
+  SPB_CHECK_CUDA(cudaGetDevice(&dev));
+  SPB_CHECK_CUDA(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10) {
+    set_error("spb_net_create: device %s is sm_%d%d; this library is built for sm_100a only", prop.name, prop.major,
+              prop.minor);
+    return SPB_EARCH;
+  }
+  Net* net = static_cast<Net*>(calloc(1, sizeof(Net)));
+  if (!net) return SPB_ENOMEM;
+  net->impl = SPB_IMPL_TCGEN05;
+  for (int li = 0; li < kNumLayers; ++li) {
+    SPB_CHECK_ARG(weights[li] && biases[li]);
+    LayerDev& L = net->layer[li];
+    const LayerSpec& S = kSpec[li];
+    L.cin = S.cin;
+    L.cout = S.cout;
+    L.ks = S.ks;
+    L.relu = S.relu;
+    L.pool = S.pool;
+    L.cout_pad = (S.cout + 15) / 16 * 16;
+    const int taps = S.ks * S.ks, K = taps * S.cin;
+    std::vector<__nv_bfloat16> ws((size_t)taps * S.cin * L.cout_pad, __float2bfloat16(0.f));
+    std::vector<__nv_bfloat16> wt((size_t)L.cout_pad * K, __float2bfloat16(0.f));
+    std::vector<float> b(L.cout_pad, 0.f);
+    const float* w = weights[li];  // OIHW
+    for (int co = 0; co < S.cout; ++co) {
+      b[co] = biases[li][co];
+      for (int ci = 0; ci < S.cin; ++ci)
+        for (int t = 0; t < taps; ++t) {
+          const __nv_bfloat16 v = __float2bfloat16_rn(w[((size_t)co * S.cin + ci) * taps + t]);
+          ws[((size_t)t * S.cin + ci) * L.cout_pad + co] = v;
+          wt[(size_t)co * K + (size_t)t * S.cin + ci] = v;
+        }
+    }
+    SPB_CHECK_CUDA(cudaMalloc(&L.bias, b.size() * sizeof(float)));
+    SPB_CHECK_CUDA(cudaMemcpy(L.bias, b.data(), b.size() * sizeof(float), cudaMemcpyHostToDevice));
+    SPB_CHECK_CUDA(cudaMalloc(&L.w_simt, ws.size() * 2));
+    SPB_CHECK_CUDA(cudaMemcpy(L.w_simt, ws.data(), ws.size() * 2, cudaMemcpyHostToDevice));
+    SPB_CHECK_CUDA(cudaMalloc(&L.w_tc, wt.size() * 2));
+    SPB_CHECK_CUDA(cudaMemcpy(L.w_tc, wt.data(), wt.size() * 2, cudaMemcpyHostToDevice));
+    if (li == 0) {
+      std::vector<float> w1(9 * 64);
+      for (int t = 0; t < 9; ++t)
+        for (int co = 0; co < 64; ++co) w1[t * 64 + co] = __bfloat162float(ws[(size_t)t * 64 + co]);
+      SPB_CHECK_CUDA(cudaMalloc(&L.w1a_f32, w1.size() * sizeof(float)));
+      SPB_CHECK_CUDA(cudaMemcpy(L.w1a_f32, w1.data(), w1.size() * sizeof(float), cudaMemcpyHostToDevice));
+    } else {
+      const int rc = conv_tc_prepare(L);
+      if (rc != SPB_OK) return rc;
+    }
+  }
+  *out = reinterpret_cast<spb_net*>(net);
+  return SPB_OK;
+}
+
+int spb_net_destroy(spb_net* h) {
+  if (!h) return SPB_OK;
+  Net* net = reinterpret_cast<Net*>(h);
+  for (int li = 0; li < kNumLayers; ++li) {
+    LayerDev& L = net->layer[li];
+    cudaFree(L.bias);
+    cudaFree(L.w_simt);
+    cudaFree(L.w_tc);
+    cudaFree(L.w1a_f32);
+    free(L.tmap_w);
+  }
+  free(net);
+  return SPB_OK;
+}
+
+int spb_net_set_impl(spb_net* h, int impl) {
+  SPB_CHECK_ARG(h && (impl == SPB_IMPL_TCGEN05 || impl == SPB_IMPL_SIMT));
+  reinterpret_cast<Net*>(h)->impl = impl;
+  return SPB_OK;
+}
+
+size_t spb_net_workspace_bytes(int B, int H, int W, int want_desc) {
+  (void)want_desc;
+  if (B < 1 || H < 8 || W < 8) return 0;
+  Workspace w(nullptr, B, H, W);
+  return w.bytes + 1024;
+}
+
+int spb_net_forward(spb_net* h, const float* x, int B, int H, int W, float* semi, float* desc, void* ws,
+                    size_t ws_bytes, void* stream) {
+  SPB_CHECK_ARG(h && x && semi && ws);
+  SPB_CHECK_ARG(B >= 1 && H >= 8 && W >= 8 && H % 8 == 0 && W % 8 == 0);
+  if (ws_bytes < spb_net_workspace_bytes(B, H, W, desc != nullptr)) {
+    set_error("spb_net_forward: workspace %zu < %zu bytes", ws_bytes, spb_net_workspace_bytes(B, H, W, desc != nullptr));
+    return SPB_ENOMEM;
+  }
+  return forward(reinterpret_cast<Net*>(h), x, B, H, W, semi, desc, align_ptr(ws), as_stream(stream));
+}
+
+int spb_net_layer(spb_net* h, int layer, const void* in, void* out, int B, int H, int W, void* stream) {
+  SPB_CHECK_ARG(h && in && out && layer >= 0 && layer < kNumLayers && B >= 1 && H >= 1 && W >= 1);
+  const int f32 = (layer == 9 || layer == 11);
+  return run_layer(reinterpret_cast<Net*>(h), layer, in, out, B, H, W, f32, 0, as_stream(stream));
+}
+
+// ---- whole HA step ----------------------------------------------------------------------------------
+static void ha_layout(int n, int H, int W, size_t& off_warp, size_t& off_semi, size_t& off_agg, size_t& off_net,
+                      size_t& total) {
+  size_t o = 0;
+  off_warp = o;
+  o += align_up((size_t)n * H * W * 4, 1024);
+  off_semi = o;
+  o += align_up((size_t)n * (H / 8) * (W / 8) * 65 * 4, 1024);
+  off_agg = o;
+  o += align_up(spb_ha_aggregate_workspace_bytes(n, H, W), 1024);
+  off_net = o;
+  o += spb_net_workspace_bytes(n, H, W, 0);
+  total = o;
+}
+
+size_t spb_ha_workspace_bytes(int N, int H, int W) {
+  if (N < 1 || H < 8 || W < 8) return 0;
+  size_t a, b, c, d, t;
+  ha_layout(N, H, W, a, b, c, d, t);
+  return t + 1024;
+}
+
+int spb_ha_heatmap_sums(spb_net* h, const float* img, const float* mats_unwarp, const float* mats_fwd, int N, int H,
+                        int W, float* sums, int accumulate, void* ws, size_t ws_bytes, void* stream) {
+  SPB_CHECK_ARG(h && img && mats_unwarp && mats_fwd && sums && ws);
+  SPB_CHECK_ARG(N >= 1 && H >= 8 && W >= 8 && H % 8 == 0 && W % 8 == 0);
+  Net* net = reinterpret_cast<Net*>(h);
+  const int chunk = (net->ha_chunk > 0 && net->ha_chunk < N) ? net->ha_chunk : N;
+  size_t o_warp, o_semi, o_agg, o_net, total;
+  ha_layout(chunk, H, W, o_warp, o_semi, o_agg, o_net, total);
+  if (ws_bytes < total + 1024) {
+    set_error("spb_ha_heatmap_sums: workspace %zu < %zu bytes", ws_bytes, total + 1024);
+    return SPB_ENOMEM;
+  }
+  char* base = static_cast<char*>(align_ptr(ws));
+  float* warped = reinterpret_cast<float*>(base + o_warp);
+  float* semi = reinterpret_cast<float*>(base + o_semi);
+  for (int n0 = 0; n0 < N; n0 += chunk) {
+    const int n = (N - n0 < chunk) ? N - n0 : chunk;
+    int rc = spb_inv_warp_image_batch(img, 0, mats_fwd + 9 * n0, warped, n, H, W, SPB_MODE_BILINEAR, stream);
+    if (rc != SPB_OK) return rc;
+    rc = forward(net, warped, n, H, W, semi, nullptr, base + o_net, as_stream(stream));
+    if (rc != SPB_OK) return rc;
+    rc = spb_ha_aggregate(semi, 65, mats_unwarp + 9 * n0, mats_fwd + 9 * n0, n, H, W, sums, accumulate || n0 > 0,
+                          base + o_agg, total - o_agg, stream);
+    if (rc != SPB_OK) return rc;
+  }
+  return SPB_OK;
+}
+
+int spb_net_set_ha_chunk(spb_net* h, int views) {
+  SPB_CHECK_ARG(h && views >= 0);
+  reinterpret_cast<Net*>(h)->ha_chunk = views;
+  return SPB_OK;
+}
+
+}  // extern "C"

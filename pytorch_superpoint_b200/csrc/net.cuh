@@ -1,0 +1,35 @@
+// Network state shared by net.cu (C ABI), conv_simt.cu and conv_tc.cu.
+#pragma once
+#include "common.cuh"
+
+namespace spb {
+
+constexpr int kNumLayers = 12;  // conv1a,1b,2a,2b,3a,3b,4a,4b,Pa,Pb,Da,Db
+
+struct LayerDev {
+  int cin, cout, ks, relu, pool;
+  int cout_pad;                // multiple of 16 (65 -> 80): SIMT quarter split and UMMA N
+  float* bias;                 // fp32 [cout_pad], zero padded
+  __nv_bfloat16* w_simt;       // bf16 [tap][cin][cout_pad]
+  __nv_bfloat16* w_tc;         // bf16 [cout_pad][tap*cin]   (K-major rows for the UMMA B operand)
+  float* w1a_f32;              // conv1a only: bf16-rounded weights as fp32 [9][64]
+  void* tmap_w;                // host copy of the CUtensorMap for w_tc (conv_tc.cu), 128 B
+};
+
+struct Net {
+  LayerDev layer[kNumLayers];
+  int impl;
+  int ha_chunk;  // views per pass in spb_ha_heatmap_sums (0 = all)
+};
+
+// conv_simt.cu
+int conv1a_simt(const LayerDev& L, const float* x, __nv_bfloat16* out, int B, int H, int W, cudaStream_t st);
+int conv_simt(const LayerDev& L, const __nv_bfloat16* in, void* out, int B, int H, int W, int out_f32, cudaStream_t st);
+int l2norm_rows(float* d, long long rows, int C, cudaStream_t st);
+
+// conv_tc.cu (tcgen05 / TMEM / TMA)
+int conv_tc_prepare(LayerDev& L);  // builds the weight tensor map after w_tc is uploaded
+int conv_tc(const LayerDev& L, const __nv_bfloat16* in, void* out, int B, int H, int W, int out_f32, int l2norm,
+            cudaStream_t st);
+
+}  // namespace spb

@@ -1,0 +1,186 @@
+"""``SuperPointNet_b200`` -- drop-in for the reference networks behind ``utils/loader.py:155-164 modelLoader``.
+
+Same constructor / ``forward`` / ``load_state_dict`` surface as ``models/SuperPointNet_gauss2.py:11-70``
+(and ``models/SuperPointNet.py``, ``models/SuperPointNet_pretrained.py``): ``forward(x[B,1,H,W])`` returns
+``{'semi': [B,65,H/8,W/8], 'desc': [B,256,H/8,W/8]}``.  Any of the three reference state-dict layouts is
+accepted; BatchNorm runs in eval mode (running statistics), folded into the conv weights -- see DESIGN.md
+for why the as-written train-mode statistics are not reproduced.  The math runs in libspb200.so
+(bf16 tcgen05 implicit-GEMM); PyTorch only owns the buffers.
+"""
+from __future__ import annotations
+
+import collections
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+LAYER_NAMES = ["conv1a", "conv1b", "conv2a", "conv2b", "conv3a", "conv3b", "conv4a", "conv4b",
+               "convPa", "convPb", "convDa", "convDb"]
+LAYER_SHAPES = [(1, 64, 3), (64, 64, 3), (64, 64, 3), (64, 64, 3), (64, 128, 3), (128, 128, 3), (128, 128, 3),
+                (128, 128, 3), (128, 256, 3), (256, 65, 1), (128, 256, 3), (256, 256, 1)]
+
+# SuperPointNet_gauss2 / unet_parts naming (models/unet_parts.py:14-21,41-44): (conv, bn) module paths
+_GAUSS2 = {
+    "conv1a": ("inc.conv.conv.0", "inc.conv.conv.1"), "conv1b": ("inc.conv.conv.3", "inc.conv.conv.4"),
+    "conv2a": ("down1.mpconv.1.conv.0", "down1.mpconv.1.conv.1"),
+    "conv2b": ("down1.mpconv.1.conv.3", "down1.mpconv.1.conv.4"),
+    "conv3a": ("down2.mpconv.1.conv.0", "down2.mpconv.1.conv.1"),
+    "conv3b": ("down2.mpconv.1.conv.3", "down2.mpconv.1.conv.4"),
+    "conv4a": ("down3.mpconv.1.conv.0", "down3.mpconv.1.conv.1"),
+    "conv4b": ("down3.mpconv.1.conv.3", "down3.mpconv.1.conv.4"),
+    "convPa": ("convPa", "bnPa"), "convPb": ("convPb", "bnPb"),
+    "convDa": ("convDa", "bnDa"), "convDb": ("convDb", "bnDb"),
+}
+
+
+def fold_state_dict(state_dict, eps: float = 1e-5):
+    """Any reference layout -> 12 (weight OIHW fp32, bias fp32) numpy pairs with eval-mode BN folded in."""
+    sd = {(k[7:] if k.startswith("module.") else k): v for k, v in state_dict.items()}
+    gauss2 = "inc.conv.conv.0.weight" in sd
+    ws, bs = [], []
+    for name, (cin, cout, ks) in zip(LAYER_NAMES, LAYER_SHAPES):
+        cname, bname = _GAUSS2[name] if gauss2 else (name, "bn" + name[4:])
+        if cname + ".weight" not in sd:
+            raise KeyError(f"state_dict has no '{cname}.weight' (not a SuperPointNet layout)")
+        w = sd[cname + ".weight"].detach().to("cpu", torch.float64)
+        b = sd[cname + ".bias"].detach().to("cpu", torch.float64)
+        if tuple(w.shape) != (cout, cin, ks, ks):
+            raise ValueError(f"{cname}.weight has shape {tuple(w.shape)}, expected {(cout, cin, ks, ks)}")
+        if bname + ".running_mean" in sd:
+            g, beta, m, v = (sd[bname + s].detach().to("cpu", torch.float64)
+                             for s in (".weight", ".bias", ".running_mean", ".running_var"))
+            s = g / torch.sqrt(v + eps)
+            w = w * s[:, None, None, None]
+            b = (b - m) * s + beta
+        ws.append(np.ascontiguousarray(w.to(torch.float32).numpy()))
+        bs.append(np.ascontiguousarray(b.to(torch.float32).numpy()))
+    return ws, bs
+
+
+class SuperPointNet_b200(nn.Module):
+    """B200-native SuperPoint network.  ``SuperPointNet_b200(subpixel_channel=1)`` like the reference."""
+
+    def __init__(self, subpixel_channel=1, impl: str = "tcgen05"):
+        super().__init__()
+        self._sd = collections.OrderedDict()
+        self._handle = None
+        self._handle_dev = None
+        self._ws = None
+        self._impl = impl
+        self.output = None
+        # default initialisation = torch's Conv2d default, gauss2 naming (reference default model)
+        for name, (cin, cout, ks) in zip(LAYER_NAMES, LAYER_SHAPES):
+            conv = nn.Conv2d(cin, cout, ks, padding=ks // 2)
+            cname, bname = _GAUSS2[name]
+            self._sd[cname + ".weight"] = conv.weight.detach().clone()
+            self._sd[cname + ".bias"] = conv.bias.detach().clone()
+            self._sd[bname + ".weight"] = torch.ones(cout)
+            self._sd[bname + ".bias"] = torch.zeros(cout)
+            self._sd[bname + ".running_mean"] = torch.zeros(cout)
+            self._sd[bname + ".running_var"] = torch.ones(cout)
+            self._sd[bname + ".num_batches_tracked"] = torch.tensor(0)
+
+    # ---- state dict: keep whatever reference layout was loaded ------------------------------------------
+    def state_dict(self, *args, **kwargs):
+        return collections.OrderedDict(self._sd)
+
+    def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
+        fold_state_dict(state_dict)  # validates names and shapes
+        self._sd = collections.OrderedDict((k, v.detach().clone().cpu()) for k, v in state_dict.items())
+        self._release()
+        return torch.nn.modules.module._IncompatibleKeys([], [])
+
+    # ---- C handle ---------------------------------------------------------------------------------------
+    def _release(self):
+        if self._handle is not None:
+            _lib.lib().spb_net_destroy(self._handle)
+        self._handle = None
+        self._ws = None
+
+    def __del__(self):
+        try:
+            self._release()
+        except Exception:
+            pass
+
+    def set_impl(self, impl: str):
+        self._impl = impl
+        if self._handle is not None:
+            _lib.check(_lib.lib().spb_net_set_impl(self._handle, {"tcgen05": 0, "simt": 1}[impl]), "net_set_impl")
+
+    def handle(self, dev: torch.device):
+        if self._handle is not None and self._handle_dev != dev:
+            self._release()
+        if self._handle is None:
+            L = _lib.lib()
+            ws, bs = fold_state_dict(self._sd)
+            arr = (C.c_void_p * 12)(*[w.ctypes.data for w in ws])
+            brr = (C.c_void_p * 12)(*[b.ctypes.data for b in bs])
+            h = C.c_void_p()
+            with torch.cuda.device(dev):
+                _lib.check(L.spb_net_create(C.byref(h), arr, brr), "net_create")
+            self._handle, self._handle_dev = h, dev
+            self.set_impl(self._impl)
+        return self._handle
+
+    def _workspace(self, nbytes: int, dev):
+        if self._ws is None or self._ws.numel() < nbytes or self._ws.device != dev:
+            self._ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+        return self._ws
+
+    # ---- forward ----------------------------------------------------------------------------------------
+    def forward_nhwc(self, x: torch.Tensor, want_desc: bool = True):
+        """x [B,1,H,W] cuda fp32 -> (semi [B,Hc,Wc,65] fp32, desc [B,Hc,Wc,256] fp32 or None)."""
+        if not x.is_cuda:
+            if not torch.cuda.is_available():
+                raise RuntimeError("SuperPointNet_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+            x = x.cuda()
+        x = x.to(torch.float32).contiguous()
+        B, ch, H, W = x.shape
+        if ch != 1 or H % 8 or W % 8:
+            raise ValueError(f"expected [B,1,H,W] with H, W multiples of 8, got {tuple(x.shape)}")
+        dev = x.device
+        h = self.handle(dev)
+        L = _lib.lib()
+        semi = torch.empty((B, H // 8, W // 8, 65), device=dev, dtype=torch.float32)
+        desc = torch.empty((B, H // 8, W // 8, 256), device=dev, dtype=torch.float32) if want_desc else None
+        nbytes = L.spb_net_workspace_bytes(B, H, W, int(want_desc))
+        ws = self._workspace(nbytes, dev)
+        with torch.cuda.device(dev):
+            _lib.check(L.spb_net_forward(h, x.data_ptr(), B, H, W, semi.data_ptr(),
+                                         desc.data_ptr() if want_desc else None, ws.data_ptr(), ws.numel(),
+                                         torch.cuda.current_stream().cuda_stream), "net_forward")
+        return semi, desc
+
+    def forward(self, x):
+        semi, desc = self.forward_nhwc(x, want_desc=True)
+        output = {"semi": semi.permute(0, 3, 1, 2), "desc": desc.permute(0, 3, 1, 2)}
+        self.output = output
+        return output
+
+    # ---- whole HA step (datasets/Coco.py:262-284 + export.py:309-310) -----------------------------------
+    def ha_heatmap_sums(self, img, mats_unwarp, mats_fwd, sums=None, accumulate=False, chunk: int = 0):
+        """img [H,W] cuda fp32; mats [N,3,3] (this rank's views) -> sums [2,H,W] (sum heat*mask, sum mask)."""
+        dev = img.device
+        H, W = img.shape[-2:]
+        mu = mats_unwarp.to(dev, torch.float32).reshape(-1, 3, 3).contiguous()
+        mf = mats_fwd.to(dev, torch.float32).reshape(-1, 3, 3).contiguous()
+        N = mu.shape[0]
+        h = self.handle(dev)
+        L = _lib.lib()
+        _lib.check(L.spb_net_set_ha_chunk(h, int(chunk)), "set_ha_chunk")
+        n_ws = chunk if 0 < chunk < N else N
+        nbytes = L.spb_ha_workspace_bytes(n_ws, H, W)
+        ws = self._workspace(nbytes, dev)
+        if sums is None:
+            sums = torch.empty((2, H, W), device=dev, dtype=torch.float32)
+            accumulate = False
+        with torch.cuda.device(dev):
+            _lib.check(L.spb_ha_heatmap_sums(h, img.contiguous().data_ptr(), mu.data_ptr(), mf.data_ptr(), N, H, W,
+                                             sums.data_ptr(), int(bool(accumulate)), ws.data_ptr(), ws.numel(),
+                                             torch.cuda.current_stream().cuda_stream), "ha_heatmap_sums")
+        return sums

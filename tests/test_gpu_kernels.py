@@ -1,0 +1,190 @@
+"""GPU parity tests: every CUDA kernel (through the C ABI) against the CPU oracle on the same seeded
+inputs, against the golden fixtures produced by the unmodified reference, and -- at full size -- through
+size-independent properties.  Run on the B200 box with ``pytest -m gpu``."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import oracle as O  # noqa: E402  (checker only)
+
+
+@pytest.fixture(scope="module")
+def spb():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import pytorch_superpoint_b200 as pkg
+    from pytorch_superpoint_b200 import _lib
+    assert _lib.lib().spb_version() >= 100  # the in-tree .so really loaded
+    return pkg
+
+
+def _mats(n, seed):
+    from pytorch_superpoint_b200.homographies import make_ha_homographies
+    return make_ha_homographies(n, seed=seed)
+
+
+# ---------------------------------------------------------------------------------------------- warp
+def test_warp_matches_oracle_bitexact(spb, golden):
+    g = golden("warp")
+    img, inv = torch.from_numpy(g["img"]).cuda(), torch.from_numpy(g["inv"]).cuda()
+    w = spb.inv_warp_image_batch(img, inv, mode="bilinear")[:, 0].cpu().numpy()
+    assert np.array_equal(w, O.inv_warp_image_batch(g["img"], g["inv"], "bilinear"))  # same fp32 op order
+    assert np.abs(w - g["warped"]).max() < 5e-5  # vs the reference itself (fp32 op-order tolerance)
+    n = spb.inv_warp_image_batch(img, inv, mode="nearest")[:, 0].cpu().numpy()
+    assert np.array_equal(n, O.inv_warp_image_batch(g["img"], g["inv"], "nearest"))
+    m = spb.compute_valid_mask((48, 64), inv).cpu().numpy()
+    assert np.array_equal(m, g["mask"])  # reference's own mask, exact
+    m2 = spb.compute_valid_mask((48, 64), inv, erosion_radius=2).cpu().numpy()
+    assert np.array_equal(m2, g["mask_e2"])
+
+
+def test_warp_batched_images_and_odd_width(spb):
+    rng = np.random.RandomState(0)
+    h, inv = _mats(5, 4)
+    imgs = rng.rand(5, 37, 53).astype(np.float32)
+    w = spb.inv_warp_image_batch(torch.from_numpy(imgs)[:, None].cuda(), torch.from_numpy(inv).cuda())
+    assert np.array_equal(w[:, 0].cpu().numpy(), O.inv_warp_image_batch(imgs, inv, "bilinear"))
+
+
+def test_valid_mask_full_size_vs_reference(spb, golden):
+    g = golden("mask_240x320_n100")
+    ref = np.unpackbits(g["mask_bits"])[: np.prod(g["shape"])].reshape(g["shape"]).astype(np.float32)
+    m = spb.compute_valid_mask((240, 320), torch.from_numpy(g["inv"]).cuda()).cpu().numpy()
+    assert np.array_equal(m, O.compute_valid_mask((240, 320), g["inv"]))
+    assert int((m != ref).sum()) <= 8
+
+
+def test_warp_degenerate_homography(spb):
+    """w -> 0 / NaN coordinates must produce zeros (zero padding), not crash."""
+    M = np.stack([np.eye(3), np.array([[1, 0, 0], [0, 1, 0], [1.0, 0, 0]]), np.zeros((3, 3))]).astype(np.float32)
+    img = np.random.RandomState(1).rand(24, 32).astype(np.float32)
+    w = spb.inv_warp_image_batch(torch.from_numpy(img).cuda(), torch.from_numpy(M).cuda())[:, 0].cpu().numpy()
+    assert np.array_equal(w, O.inv_warp_image_batch(img, M, "bilinear"))
+    assert np.all(w[2] == 0)
+
+
+# ---------------------------------------------------------------------------------------------- heat
+def test_flatten_detection(spb, golden):
+    g = golden("heat")
+    semi = torch.from_numpy(g["semi"]).cuda()
+    h = spb.flattenDetection(semi, tensor=True)[:, 0].cpu().numpy()
+    assert np.abs(h - g["heat"]).max() < 1e-6
+    assert np.abs(h - O.flatten_detection(g["semi"])).max() < 1e-6
+    h1 = spb.flattenDetection(semi[0], tensor=True).cpu().numpy()
+    assert h1.shape == (1, 48, 64) and np.array_equal(h1[0], h[0])
+
+
+def test_combine_heatmap(spb, golden):
+    g = golden("heat")
+    out = spb.combine_heatmap(torch.from_numpy(g["heat"])[:, None].cuda(), torch.from_numpy(g["h"])[None].cuda(),
+                              torch.from_numpy(g["mask"])[:, None].cuda())[0].cpu().numpy()
+    assert np.array_equal(out, O.combine_heatmap(g["heat"], g["h"], g["mask"]))  # same op order: bit-exact
+    assert np.abs(out - g["combined"]).max() < 2e-5
+
+
+@pytest.mark.parametrize("H,W,N,seed", [(48, 64, 6, 3), (64, 96, 13, 5), (240, 320, 100, 0)])
+def test_fused_aggregate(spb, H, W, N, seed):
+    """spb_ha_aggregate == flattenDetection * valid_mask -> combine_heatmap of the oracle."""
+    from pytorch_superpoint_b200 import ops
+    h, inv = _mats(N, seed)
+    semi = (torch.randn(N, 65, H // 8, W // 8, generator=torch.Generator().manual_seed(seed)) * 2).numpy()
+    nhwc = torch.from_numpy(np.ascontiguousarray(semi.transpose(0, 2, 3, 1))).cuda()
+    sums = ops.ha_aggregate(nhwc, torch.from_numpy(h), torch.from_numpy(inv), H, W)
+    heat = ops.ha_finalize(sums).cpu().numpy()
+    if N <= 16:
+        ref = O.combine_heatmap(O.flatten_detection(semi), h, O.compute_valid_mask((H, W), inv))
+    else:  # full size: use the (already verified) unfused CUDA kernels as the comparison path
+        hm = spb.flattenDetection(torch.from_numpy(semi).cuda(), tensor=True)
+        mk = spb.compute_valid_mask((H, W), torch.from_numpy(inv).cuda())[:, None]
+        ref = spb.combine_heatmap(hm, torch.from_numpy(h)[None].cuda(), mk)[0].cpu().numpy()
+    ok = np.isfinite(ref)
+    assert np.array_equal(np.isfinite(heat), ok)
+    assert np.abs(heat[ok] - ref[ok]).max() < 2e-6
+    # chunked accumulation gives the same sums
+    k = N // 2
+    s2 = ops.ha_aggregate(nhwc[:k].contiguous(), torch.from_numpy(h[:k]), torch.from_numpy(inv[:k]), H, W)
+    s2 = ops.ha_aggregate(nhwc[k:].contiguous(), torch.from_numpy(h[k:]), torch.from_numpy(inv[k:]), H, W, sums=s2,
+                          accumulate=True)
+    assert torch.allclose(s2, sums, rtol=1e-5, atol=1e-6)
+
+
+def test_fused_aggregate_extreme_scale_fallback(spb):
+    """A strongly magnifying un-warp makes a 16x16 tile cover > 64 cells: exercises the global fallback path."""
+    from pytorch_superpoint_b200 import ops
+    H, W, N = 96, 128, 3
+    s = np.array([[6.0, 0, 0], [0, 6.0, 0], [0, 0, 1]], np.float32)
+    h = np.stack([np.eye(3, dtype=np.float32), s, np.linalg.inv(s).astype(np.float32)])
+    inv = np.stack([np.linalg.inv(x) for x in h]).astype(np.float32)
+    semi = (torch.randn(N, 65, H // 8, W // 8, generator=torch.Generator().manual_seed(2)) * 2).numpy()
+    nhwc = torch.from_numpy(np.ascontiguousarray(semi.transpose(0, 2, 3, 1))).cuda()
+    heat = ops.ha_finalize(ops.ha_aggregate(nhwc, torch.from_numpy(h), torch.from_numpy(inv), H, W)).cpu().numpy()
+    ref = O.combine_heatmap(O.flatten_detection(semi), h, O.compute_valid_mask((H, W), inv))
+    assert np.abs(heat - ref).max() < 2e-6
+
+
+# ---------------------------------------------------------------------------------------------- NMS
+CASES = ["smooth_96x128", "flat_random_240x320", "sparse_64x80", "ties_72x88", "empty_40x48", "single_40x48",
+         "border_40x48"]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_get_pts_golden_bit_exact(spb, golden, case):
+    g = golden("pts")
+    pts = spb.getPtsFromHeatmap(torch.from_numpy(g["heat_" + case]).cuda(), 0.015, 4)
+    ref = g["pts_" + case]
+    assert pts.shape == ref.shape and pts.dtype == np.float64
+    assert np.array_equal(pts, ref)
+
+
+@pytest.mark.parametrize("H,W,dist,thr", [(240, 320, 4, 0.015), (480, 640, 4, 0.015), (384, 1248, 4, 0.015),
+                                          (120, 160, 1, 0.3), (64, 64, 0, 0.5), (96, 100, 8, 0.1)])
+def test_get_pts_vs_oracle_random(spb, H, W, dist, thr):
+    rng = np.random.RandomState(H + W + dist)
+    import cv2
+    heat = cv2.GaussianBlur(rng.rand(H, W).astype(np.float32), (5, 5), 0)
+    heat = (heat * (2 * thr)).astype(np.float32)
+    pts = spb.getPtsFromHeatmap(torch.from_numpy(heat).cuda(), thr, dist)
+    assert np.array_equal(pts, O.get_pts_from_heatmap(heat, thr, dist))
+
+
+def test_get_pts_batch_topk_and_properties(spb):
+    from pytorch_superpoint_b200 import ops
+    rng = np.random.RandomState(3)
+    heat = (0.0154 + 0.002 * rng.randn(8, 240, 320)).astype(np.float32)  # random-init-like near-uniform maps
+    pts, counts, total = ops.get_pts_from_heatmap_device(torch.from_numpy(heat).cuda(), 0.015, 4, 4, top_k=600)
+    pts, counts, total = pts.cpu().numpy(), counts.cpu().numpy(), total.cpu().numpy()
+    for b in range(8):
+        ref = O.get_pts_from_heatmap(heat[b], 0.015, 4).T
+        assert total[b] == ref.shape[0] and counts[b] == min(600, ref.shape[0])
+        assert np.array_equal(pts[b, :counts[b]].astype(np.float64), ref[:600])
+        p = pts[b, :counts[b]]
+        assert np.all(np.diff(p[:, 2]) <= 0)  # sorted
+        assert p[:, 0].min() >= 4 and p[:, 0].max() < 316 and p[:, 1].min() >= 4 and p[:, 1].max() < 236
+        d = np.abs(p[:, None, :2] - p[None, :, :2]).max(-1) + 1e9 * np.eye(len(p))
+        assert d.min() > 4  # pairwise Chebyshev distance > nms_dist
+    # idempotence: NMS of the kept points' sparse map keeps exactly those points
+    sp = np.zeros((240, 320), np.float32)
+    full = O.get_pts_from_heatmap(heat[0], 0.015, 4)
+    sp[full[1].astype(int), full[0].astype(int)] = full[2]
+    again = spb.getPtsFromHeatmap(torch.from_numpy(sp).cuda(), 0.015, 4)
+    assert np.array_equal(again, full)
+
+
+# ---------------------------------------------------------------------------------------------- descriptors
+def test_sample_desc(spb, golden):
+    g = golden("desc")
+    d = spb.sample_desc_from_points(torch.from_numpy(g["coarse"]).cuda(), g["pts"])
+    assert d.shape == g["desc"].shape and d.dtype == np.float32
+    assert np.abs(d - g["desc"]).max() < 1e-6
+    cos = (d * g["desc"]).sum(0)
+    assert cos.min() > 0.999999
+    assert spb.sample_desc_from_points(torch.from_numpy(g["coarse"]).cuda(), np.zeros((3, 0))).shape == (256, 0)
+    # NHWC device path == NCHW path
+    from pytorch_superpoint_b200 import ops
+    p = torch.from_numpy(np.ascontiguousarray(g["pts"].T)).float().cuda()
+    c = torch.from_numpy(g["coarse"]).cuda()[0]
+    a = ops.sample_desc_device(c, p, nhwc=False)
+    b = ops.sample_desc_device(c.permute(1, 2, 0).contiguous(), p, nhwc=True)
+    assert torch.equal(a, b)

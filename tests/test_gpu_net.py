@@ -1,0 +1,128 @@
+"""GPU parity tests for the network kernels: tcgen05 implicit-GEMM vs the CUDA-core validation kernels
+(same bf16 numerics -> tight), and both vs the fp32 CPU oracle / the reference's golden outputs
+(bf16 tolerance: heat-map max-abs 1e-2, descriptor cosine >= 0.999 -- BASELINE.json north_star)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import oracle as O  # noqa: E402  (checker only)
+
+SHAPES = [(1, 64, 3), (64, 64, 3), (64, 64, 3), (64, 64, 3), (64, 128, 3), (128, 128, 3), (128, 128, 3),
+          (128, 128, 3), (128, 256, 3), (256, 65, 1), (128, 256, 3), (256, 256, 1)]
+POOL = [0, 1, 0, 1, 0, 1, 0, 0, 0, 0, 0, 0]
+
+
+@pytest.fixture(scope="module")
+def net():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from pytorch_superpoint_b200 import SuperPointNet_b200
+    n = SuperPointNet_b200()
+    n.load_state_dict(O.synthetic_state_dict("gauss2", seed=1))
+    return n
+
+
+def _layer(net, li, x, B, H, W, impl, halo=1):
+    from pytorch_superpoint_b200 import _lib
+    L = _lib.lib()
+    h = net.handle(x.device)
+    net.set_impl(impl)
+    L.spb_conv_tc_set_halo(halo)
+    cin, cout, _ = SHAPES[li]
+    oh, ow = (H // 2, W // 2) if POOL[li] else (H, W)
+    out = torch.full((B, oh, ow, cout), float("nan"), device=x.device,
+                     dtype=torch.float32 if li in (9, 11) else torch.bfloat16)
+    _lib.check(L.spb_net_layer(h, li, x.data_ptr(), out.data_ptr(), B, H, W, torch.cuda.current_stream().cuda_stream),
+               f"net_layer {li}")
+    torch.cuda.synchronize()
+    L.spb_conv_tc_set_halo(1)
+    return out
+
+
+def _ref_layer(li, x_nhwc, params):
+    """fp32 torch reference of one layer on the bf16-rounded inputs/weights (tight comparison target)."""
+    name = O.LAYERS[li][0]
+    p = O.fold_bn(params)[name]
+    w = p["w"].to(torch.bfloat16).float().cuda()
+    y = torch.nn.functional.conv2d(x_nhwc.float().permute(0, 3, 1, 2), w, p["b"].cuda(), padding=w.shape[-1] // 2)
+    if O.LAYERS[li][4]:
+        y = torch.relu(y)
+    if O.LAYERS[li][5]:
+        y = torch.nn.functional.max_pool2d(y, 2, 2)
+    return y.permute(0, 2, 3, 1).contiguous()
+
+
+# 1x1 layers first: they exercise TMA/UMMA/TMEM plumbing with the canonical (unshifted) operand layout
+@pytest.mark.parametrize("halo", [0, 1])
+@pytest.mark.parametrize("li,B,H,W", [(9, 2, 32, 40), (11, 2, 32, 40), (9, 3, 30, 40), (1, 2, 32, 48), (2, 2, 32, 40),
+                                      (3, 1, 60, 80), (4, 2, 30, 40), (5, 2, 60, 80), (6, 3, 30, 40), (7, 1, 16, 8),
+                                      (8, 2, 30, 40), (10, 1, 30, 40), (1, 1, 240, 320)])
+def test_tcgen05_layer_vs_reference(net, li, B, H, W, halo):
+    if SHAPES[li][2] == 1 and halo == 0:
+        pytest.skip("1x1 layers have a single operand layout")
+    torch.manual_seed(li * 7 + B)
+    cin = SHAPES[li][0]
+    x = (torch.randn(B, H, W, cin, device="cuda") * 0.5).to(torch.bfloat16).contiguous()
+    params = O.canonical_params(O.synthetic_state_dict("gauss2", seed=1))
+    ref = _ref_layer(li, x, params)
+    simt = _layer(net, li, x, B, H, W, "simt").float()
+    tc = _layer(net, li, x, B, H, W, "tcgen05", halo).float()
+    tol = 3e-2 if li not in (9, 11) else 2e-3  # bf16 output rounding (|y| <~ 4) vs fp32 outputs
+    assert torch.isfinite(simt).all() and torch.isfinite(tc).all()
+    assert (simt - ref).abs().max().item() < tol, "SIMT validation kernel vs torch"
+    assert (tc - ref).abs().max().item() < tol, "tcgen05 kernel vs torch"
+    # same numerics contract -> the two CUDA paths agree to accumulation-order noise (1 bf16 ulp at most)
+    assert (tc - simt).abs().max().item() <= (3.2e-2 if li not in (9, 11) else 1e-4)
+
+
+@pytest.mark.parametrize("impl", ["simt", "tcgen05"])
+@pytest.mark.parametrize("layout", ["gauss2", "bnflat", "v1"])
+def test_forward_vs_reference_golden(impl, layout, golden):
+    """Full network on the reference's golden input (eval-mode BN): semi/desc within bf16 tolerance."""
+    from pytorch_superpoint_b200 import SuperPointNet_b200, flattenDetection
+    g = golden("net")
+    n = SuperPointNet_b200(impl=impl)
+    n.load_state_dict(O.synthetic_state_dict(layout, seed=1))
+    out = n(torch.from_numpy(g["x"]).cuda())
+    semi, desc = out["semi"], out["desc"]
+    assert tuple(semi.shape) == g[f"{layout}_eval_semi"].shape and tuple(desc.shape) == g[f"{layout}_eval_desc"].shape
+    ref_semi = torch.from_numpy(g[f"{layout}_eval_semi"]).cuda()
+    ref_desc = torch.from_numpy(g[f"{layout}_eval_desc"]).cuda()
+    heat, ref_heat = flattenDetection(semi.contiguous(), True), flattenDetection(ref_semi, True)
+    assert (heat - ref_heat).abs().max().item() < 1e-2          # north_star: max-abs 1e-2 heat-map in bf16
+    cos = (desc * ref_desc).sum(1)
+    assert cos.min().item() > 0.999                              # north_star: descriptor cosine >= 0.999
+    assert (desc.norm(dim=1) - 1).abs().max().item() < 1e-4
+
+
+def test_forward_full_size_simt_vs_tcgen05(net):
+    """240x320 batch: the two CUDA implementations agree; outputs finite; batch independence."""
+    x = torch.rand(4, 1, 240, 320, device="cuda", generator=torch.Generator("cuda").manual_seed(0))
+    net.set_impl("simt")
+    s0, d0 = net.forward_nhwc(x)
+    net.set_impl("tcgen05")
+    s1, d1 = net.forward_nhwc(x)
+    assert torch.isfinite(s1).all() and torch.isfinite(d1).all()
+    assert (s0 - s1).abs().max().item() < 5e-2
+    assert (d0 * d1).sum(-1).min().item() > 0.9995
+    s2, _ = net.forward_nhwc(x[2:3].contiguous())
+    assert torch.equal(s2[0], s1[2])
+
+
+def test_ha_end_to_end_vs_reference_golden(golden):
+    """Whole HA step (warp -> net -> fused aggregate -> NMS) on the reference's golden image."""
+    from pytorch_superpoint_b200 import SuperPointNet_b200, getPtsFromHeatmap
+    from pytorch_superpoint_b200.ops import ha_finalize
+    g = golden("ha_e2e")
+    n = SuperPointNet_b200()
+    n.load_state_dict(O.synthetic_state_dict("gauss2", seed=2))
+    img = torch.from_numpy(g["img"]).cuda()
+    for chunk in (0, 3):
+        sums = n.ha_heatmap_sums(img, torch.from_numpy(g["h"]), torch.from_numpy(g["inv"]), chunk=chunk)
+        heat = ha_finalize(sums)
+        assert (heat - torch.from_numpy(g["agg"]).cuda()).abs().max().item() < 1e-2
+    # bit-exact key-points GIVEN the reference's heat-map
+    pts = getPtsFromHeatmap(torch.from_numpy(g["agg"]).cuda(), 0.015, 4).T[:600]
+    assert np.array_equal(pts, g["pts"])
