@@ -1,0 +1,301 @@
+#!/usr/bin/env python
+"""bench.py -- HA-export throughput (BASELINE.json metric) on N B200s, one process per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path over one batch of synthetic input: IMAGES 240x320 images, each
+homography-adapted with 100 homographies (configs[1]: magicpoint_coco_export.yaml shape): image warp x100 ->
+detector network -> fused softmax/d2s/un-warp/aggregate -> (NCCL all-reduce when the homographies are sharded
+over ranks) -> divide -> threshold + greedy NMS + top-600.  Rank 0 prints ONE JSON line.
+
+  value      images/s with inputs resident in HBM (CUDA events, barrier + synchronize both sides, max over ranks)
+  e2e        same metric through HAExporter.export_batch with pinned HOST images in and HOST key-points out
+  roofline   the dominant kernel (conv_tc 64->64 3x3: conv1b) against the measured bf16 tensor peak
+  cpu_baseline  the CPU oracle port of the reference path on this box's host cores (rank 0, N=1 only)
+  --impl reference   times that CPU arm as the main line (bounded sample per step)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H, W, NVIEWS, TOPK, THR, NMS = 240, 320, 100, 600, 0.015, 4
+METRIC = "ha_export_images_per_s"
+UNIT = "images/s"
+WORKLOAD = ("HA export: 100 homographies x 240x320 (configs[1], magicpoint_coco_export.yaml shape); "
+            "SuperPointNet_gauss2 weights, seeded random init, eval-mode BN folded; thr 0.015, nms 4, top_k 600")
+CONV_GFLOP_DET = 12.161  # conv FLOPs per 240x320 view, detector path only
+
+
+def structured_images(n, seed=0):
+    """Seeded synthetic images with edges/corners (random rectangles + noise), fp32 in [0,1]."""
+    rng = np.random.RandomState(seed)
+    out = np.empty((n, H, W), np.float32)
+    for i in range(n):
+        img = np.full((H, W), 0.35, np.float32) + 0.03 * rng.randn(H, W).astype(np.float32)
+        for _ in range(14):
+            x0, y0 = rng.randint(0, W - 10), rng.randint(0, H - 10)
+            x1, y1 = x0 + rng.randint(8, W // 3), y0 + rng.randint(8, H // 3)
+            img[y0:y1, x0:x1] = rng.uniform(0, 1)
+        out[i] = np.clip(img, 0, 1)
+    return out
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["bf16_tflops_sustained"]), float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json, sustained)"
+    except Exception:
+        return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for j, n in enumerate(names) if any(len(r) >= 6 and r[2 + j].startswith("Active") for r in self.rows)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference's path (oracle/ is test infrastructure; here it is the thing TIMED
+# as the CPU baseline, never part of the GPU path)
+# ------------------------------------------------------------------------------------------------------------
+def cpu_step(params, img, mu, mf, views):
+    from oracle import oracle as O
+    return O.ha_export_one(img, mu[:views], mf[:views], params, THR, NMS, TOPK)
+
+
+def run_reference(args):
+    from oracle import oracle as O
+    from pytorch_superpoint_b200.homographies import make_ha_homographies
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    params = O.canonical_params(O.synthetic_state_dict("gauss2", seed=1))
+    imgs = structured_images(2, seed=0)
+    mu, mf = make_ha_homographies(NVIEWS, seed=0)
+    views = args.ref_views
+    for i in range(args.warmup):
+        cpu_step(params, imgs[i % 2], mu, mf, views)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        cpu_step(params, imgs[i % 2], mu, mf, views)
+    dt = (time.perf_counter() - t0) / args.steps
+    value = 1.0 / (dt * NVIEWS / views)
+    sample = (f"{views} of the {NVIEWS} homographies of one 240x320 image per step (warp, mask, net fp32, flatten, "
+              f"combine, NMS), time scaled x{NVIEWS / views:g} to a full image")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "views_per_step": views},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch.distributed as dist
+    from pytorch_superpoint_b200 import SuperPointNet_b200, _lib
+    from pytorch_superpoint_b200.synthetic import synthetic_state_dict
+    from pytorch_superpoint_b200.export import HAExporter
+    from pytorch_superpoint_b200.homographies import make_ha_homographies
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = _lib.lib()
+
+    net = SuperPointNet_b200()
+    net.load_state_dict(synthetic_state_dict("gauss2", seed=1))
+    exporter = HAExporter(net, THR, NMS, TOPK, device=dev, chunk=args.chunk)
+    B = args.images
+    imgs_np = structured_images(B, seed=0)
+    mu_np, mf_np = make_ha_homographies(NVIEWS, seed=0)  # pre-sampled outside the timed region
+    imgs_host = [torch.from_numpy(imgs_np[b]).pin_memory() for b in range(B)]
+    mu_host, mf_host = torch.from_numpy(mu_np).pin_memory(), torch.from_numpy(mf_np).pin_memory()
+    imgs_dev = torch.from_numpy(imgs_np).to(dev)
+    mu_dev, mf_dev = mu_host.to(dev), mf_host.to(dev)
+    from pytorch_superpoint_b200 import ops
+
+    def step_resident():
+        heat = exporter.heatmaps(imgs_dev, mu_dev, mf_dev)
+        mine = [b for b in range(B) if b % world == rank]
+        if mine:
+            sel = heat[mine] if len(mine) < B else heat
+            return ops.get_pts_from_heatmap_device(sel.contiguous(), THR, NMS, 4, TOPK, TOPK)
+        return None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    launches0 = L.spb_launch_count()
+    with ClockSampler(local) as clk:
+        ms = timed(step_resident, args.steps)
+    launches = int(L.spb_launch_count() - launches0)
+    value = B * args.steps / (ms / 1e3)
+
+    # ---- end to end through the public API: pinned host images in, host key-points out ------------------
+    def step_e2e():
+        exporter.export_batch(imgs_host, mu_host, mf_host, sync=True)
+
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    e2e_value = B * args.steps / (ms_e2e / 1e3)
+    h2d = B * H * W * 4 + 2 * NVIEWS * 9 * 4
+    d2h = -(-B // world) * (TOPK * 3 * 4 + 4)
+
+    # ---- roofline of the dominant kernel: a profiled pass (CUDA events around every stage launch) -------
+    h = net.handle(dev)
+    _lib.check(L.spb_net_profile(h, 1))
+    prof_steps = min(args.steps, 5)
+    ms_prof = timed(step_resident, prof_steps)
+    import ctypes as C
+    st_ms, st_n = (C.c_float * 16)(), (C.c_int * 16)()
+    _lib.check(L.spb_net_profile_read(h, st_ms, st_n))
+    _lib.check(L.spb_net_profile(h, 0))
+    names = ["conv1a", "conv1b", "conv2a", "conv2b", "conv3a", "conv3b", "conv4a", "conv4b", "convPa", "convPb",
+             "convDa", "convDb", "warp", "aggregate"]
+    stage_ms = {names[i]: round(st_ms[i] / prof_steps, 4) for i in range(14) if st_n[i]}
+    from pytorch_superpoint_b200.sharding import shard_bounds
+    lo, hi = shard_bounds(NVIEWS, rank, world)
+    views_local = hi - lo
+    peak_tf, peak_hbm, peak_src = peaks()
+    k_launches = st_n[1]
+    k_ms = st_ms[1] / max(k_launches, 1)
+    flop_per_launch = 2.0 * H * W * 64 * 64 * 9 * (B * views_local * prof_steps / max(k_launches, 1))
+    achieved = flop_per_launch / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
+    net_ms = sum(st_ms[i] for i in range(12)) / prof_steps
+    roofline = {"bound": "tensor", "kernel": "conv_tc_kernel<Cin64,Cout64,3x3,halo> (conv1b: 43.5% of conv FLOPs)",
+                "achieved": round(achieved, 2), "peak": peak_tf, "unit": "TFLOP/s", "frac": round(achieved / peak_tf, 4),
+                "traffic": None, "peak_source": peak_src, "avg_launch_ms": round(k_ms, 4), "launches": int(k_launches),
+                "whole_net_tflops": round(CONV_GFLOP_DET * 1e-3 * B * views_local / (net_ms * 1e-3), 2) if net_ms else None}
+
+    line = {"metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "images_per_step": B, "homographies": NVIEWS,
+                       "parallelism": f"homography-sharded x{world}, 1 NCCL all-reduce of [B,2,H,W] per step",
+                       "l2": "per-image activation working set ~1.3 GB streams through the 126 MB L2 every step "
+                             "(inputs larger than L2; no explicit flush)", "ha_chunk": args.chunk},
+            "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": round(ms_e2e / args.steps, 4)},
+            "gpu_launches": launches, "roofline": roofline, "stage_ms_per_step": stage_ms,
+            "profiled_ms_per_step": round(ms_prof / prof_steps, 4), "clocks": clk.summary()}
+
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle import oracle as O  # the CPU baseline leg: the one place this arm touches oracle/
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        params = O.canonical_params(synthetic_state_dict("gauss2", seed=1))
+        cpu_step(params, imgs_np[0], mu_np, mf_np, 5)  # warm-up
+        t0 = time.perf_counter()
+        pts_cpu = cpu_step(params, imgs_np[0], mu_np, mf_np, NVIEWS)
+        dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": round(1.0 / dt, 4), "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": "one full 240x320 image with all 100 homographies through oracle/ "
+                                          "(numpy warp/mask/combine/NMS + torch fp32 conv on all host threads)"}
+        # the same image through the GPU path: key-point overlap with the fp32 CPU oracle (informational)
+        pts_gpu = exporter.export_image(imgs_host[0], mu_host, mf_host)
+        a = {(int(x), int(y)) for x, y, _ in pts_gpu}
+        b = {(int(x), int(y)) for x, y, _ in pts_cpu}
+        line["keypoint_jaccard_vs_cpu_fp32"] = round(len(a & b) / max(len(a | b), 1), 4)
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--images", type=int, default=8, help="images per step")
+    ap.add_argument("--chunk", type=int, default=0, help="views per network pass (0 = all of the rank's views)")
+    ap.add_argument("--ref-views", type=int, default=20, help="--impl reference: homographies per step (bounded sample)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -39,6 +39,8 @@ extern "C" {
 
 int spb_version(void);
 const char* spb_last_error_string(void);
+/* number of CUDA kernels this library has launched in this process (all entry points) */
+unsigned long long spb_launch_count(void);
 
 /* ---- (1) homography warp ------------------------------------------------------------------------
  * utils/utils.py:318-351 `inv_warp_image_batch(img, mat_homo_inv, device, mode)` incl. warp_points
@@ -98,6 +100,13 @@ int spb_get_pts_from_heatmap(const float* heat, int B, int H, int W, float conf_
 int spb_sample_desc_from_points(const float* coarse, int nhwc, const float* pts, const int* count, int K,
                                 int Hc, int Wc, int D, int cell, float* out, void* stream);
 
+/* NEXT row f-1b -- models/model_wrap.py:200-234 `soft_argmax_points` (+ utils/losses.py:48-129): per key-point
+ * soft-argmax offset over the patch_size x patch_size (odd, <= 7) heat-map patch.  dxdy [K,2] fp32; the
+ * refined point is (x + dx - patch_size/2, y + dy - patch_size/2).  torchgeometry's SpatialSoftArgmax2d is
+ * restated from its published definition (package not vendored by the reference): parity unpinned. */
+int spb_soft_argmax_points(const float* heat, int H, int W, const float* pts, const int* count, int K,
+                           int patch_size, float* dxdy, void* stream);
+
 /* ---- (2) network ------------------------------------------------------------------------------------
  * models/SuperPointNet_pretrained.py:46-76, SuperPointNet_gauss2.py:43-70, SuperPointNet.py:154-224.
  * weights/biases: HOST pointers, 12 layers in the order conv1a,1b,2a,2b,3a,3b,4a,4b,Pa,Pb,Da,Db;
@@ -109,6 +118,12 @@ int spb_net_set_impl(spb_net* net, int impl); /* SPB_IMPL_* (default TCGEN05) */
 /* views processed per pass by spb_ha_heatmap_sums (0 = all N at once); bounds the workspace and lets
  * the inter-layer activations of a pass stay L2-resident */
 int spb_net_set_ha_chunk(spb_net* net, int views);
+/* Measurement hooks (bench.py roofline): record CUDA events on the launch stream around every stage
+ * (0..11 = layers conv1a..convDb, 12 = image warp, 13 = fused aggregate) while on != 0;
+ * spb_net_profile_read synchronises those events, returns summed milliseconds and launch counts per
+ * stage (arrays of 16) and clears the log. */
+int spb_net_profile(spb_net* net, int on);
+int spb_net_profile_read(spb_net* net, float* ms, int* counts);
 size_t spb_net_workspace_bytes(int B, int H, int W, int want_desc);
 /* x [B,1,H,W] fp32 (H, W multiples of 8) -> semi NHWC fp32 [B,H/8,W/8,65];
  * desc NHWC fp32 [B,H/8,W/8,256], L2-normalised over channels (NULL: detector head only). */

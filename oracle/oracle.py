@@ -267,8 +267,9 @@ def soft_argmax_points(heat: np.ndarray, pts: np.ndarray, patch_size: int = 5) -
         x, y = int(round(pts[0, k])), int(round(pts[1, k]))
         p = pad[y:y + patch_size, x:x + patch_size].astype(f32)
         p = p / (p.sum() + f32(1e-6))
-        p = np.where(p <= 0, f32(1e-6), p)
-        lg = np.log(p)
+        p = np.where(p < 0, f32(1e-6), p)  # utils/losses.py:126-129: negatives only; log(0) = -inf
+        with np.errstate(divide='ignore'):
+            lg = np.log(p)
         e = np.exp(lg - lg.max())
         den = e.sum() + f32(1e-6)
         gy, gx = np.mgrid[0:patch_size, 0:patch_size].astype(f32)

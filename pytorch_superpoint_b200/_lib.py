@@ -22,6 +22,7 @@ _ll = C.c_longlong
 PROTOTYPES = {
     "spb_version": (_i, []),
     "spb_last_error_string": (C.c_char_p, []),
+    "spb_launch_count": (C.c_ulonglong, []),
     "spb_inv_warp_image_batch": (_i, [_p, _ll, _p, _p, _i, _i, _i, _i, _p]),
     "spb_compute_valid_mask": (_i, [_p, _p, _i, _i, _i, _p]),
     "spb_flatten_detection": (_i, [_p, _i, _p, _i, _i, _i, _p]),
@@ -32,10 +33,13 @@ PROTOTYPES = {
     "spb_nms_workspace_bytes": (_z, [_i, _i, _i, _i]),
     "spb_get_pts_from_heatmap": (_i, [_p, _i, _i, _i, _f, _i, _i, _i, _i, _p, _p, _p, _p, _z, _p]),
     "spb_sample_desc_from_points": (_i, [_p, _i, _p, _p, _i, _i, _i, _i, _i, _p, _p]),
+    "spb_soft_argmax_points": (_i, [_p, _i, _i, _p, _p, _i, _i, _p, _p]),
     "spb_net_create": (_i, [C.POINTER(_p), C.POINTER(_p), C.POINTER(_p)]),
     "spb_net_destroy": (_i, [_p]),
     "spb_net_set_impl": (_i, [_p, _i]),
     "spb_net_set_ha_chunk": (_i, [_p, _i]),
+    "spb_net_profile": (_i, [_p, _i]),
+    "spb_net_profile_read": (_i, [_p, _p, _p]),
     "spb_net_workspace_bytes": (_z, [_i, _i, _i, _i]),
     "spb_net_forward": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _z, _p]),
     "spb_net_layer": (_i, [_p, _i, _p, _p, _i, _i, _i, _p]),

@@ -30,7 +30,12 @@ void set_error(const char* fmt, ...);
     }                                                                                  \
   } while (0)
 
-#define SPB_CHECK_LAUNCH() SPB_CHECK_CUDA(cudaGetLastError())
+extern unsigned long long g_launches;  // kernels launched by this library (bench.py's gpu_launches)
+#define SPB_CHECK_LAUNCH()                                   \
+  do {                                                       \
+    __atomic_fetch_add(&spb::g_launches, 1ull, __ATOMIC_RELAXED); \
+    SPB_CHECK_CUDA(cudaGetLastError());                      \
+  } while (0)
 
 // ---- coordinates ---------------------------------------------------------------------------------
 // Bit-exact restatement of the reference's coordinate pipeline (utils/utils.py:286-314,341-344 +

@@ -36,9 +36,38 @@ struct Workspace {  // carve-up of the caller's buffer for a batch of B views at
   }
 };
 
+// ---- optional per-stage CUDA-event timing (events are recorded on the launch stream) -------------------
+struct StageTimer {
+  Net* net;
+  ProfRec* r;
+  cudaStream_t st;
+  StageTimer(const Net* n, int stage, cudaStream_t s) : net(const_cast<Net*>(n)), r(nullptr), st(s) {
+    if (!net->profile) return;
+    if (net->usedrecs == net->nrecs) {
+      if (net->nrecs == net->caprecs) {
+        const int cap = net->caprecs ? net->caprecs * 2 : 256;
+        ProfRec* nr = static_cast<ProfRec*>(realloc(net->recs, cap * sizeof(ProfRec)));
+        if (!nr) return;
+        net->recs = nr;
+        net->caprecs = cap;
+      }
+      ProfRec& x = net->recs[net->nrecs];
+      if (cudaEventCreate(&x.a) != cudaSuccess || cudaEventCreate(&x.b) != cudaSuccess) return;
+      net->nrecs++;
+    }
+    r = &net->recs[net->usedrecs++];
+    r->stage = stage;
+    cudaEventRecord(r->a, st);
+  }
+  ~StageTimer() {
+    if (r) cudaEventRecord(r->b, st);
+  }
+};
+
 static int run_layer(const Net* net, int li, const void* in, void* out, int B, int H, int W, int out_f32, int l2norm,
                      cudaStream_t st) {
   const LayerDev& L = net->layer[li];
+  StageTimer tm(net, li, st);
   if (li == 0) return conv1a_simt(L, static_cast<const float*>(in), static_cast<__nv_bfloat16*>(out), B, H, W, st);
   if (net->impl == SPB_IMPL_TCGEN05)
     return conv_tc(L, static_cast<const __nv_bfloat16*>(in), out, B, H, W, out_f32, l2norm, st);
@@ -147,6 +176,11 @@ int spb_net_destroy(spb_net* h) {
     cudaFree(L.w1a_f32);
     free(L.tmap_w);
   }
+  for (int i = 0; i < net->nrecs; ++i) {
+    cudaEventDestroy(net->recs[i].a);
+    cudaEventDestroy(net->recs[i].b);
+  }
+  free(net->recs);
   free(net);
   return SPB_OK;
 }
@@ -220,14 +254,48 @@ int spb_ha_heatmap_sums(spb_net* h, const float* img, const float* mats_unwarp, 
   float* semi = reinterpret_cast<float*>(base + o_semi);
   for (int n0 = 0; n0 < N; n0 += chunk) {
     const int n = (N - n0 < chunk) ? N - n0 : chunk;
-    int rc = spb_inv_warp_image_batch(img, 0, mats_fwd + 9 * n0, warped, n, H, W, SPB_MODE_BILINEAR, stream);
+    int rc;
+    {
+      StageTimer tm(net, 12, as_stream(stream));
+      rc = spb_inv_warp_image_batch(img, 0, mats_fwd + 9 * n0, warped, n, H, W, SPB_MODE_BILINEAR, stream);
+    }
     if (rc != SPB_OK) return rc;
     rc = forward(net, warped, n, H, W, semi, nullptr, base + o_net, as_stream(stream));
     if (rc != SPB_OK) return rc;
-    rc = spb_ha_aggregate(semi, 65, mats_unwarp + 9 * n0, mats_fwd + 9 * n0, n, H, W, sums, accumulate || n0 > 0,
-                          base + o_agg, total - o_agg, stream);
+    {
+      StageTimer tm(net, 13, as_stream(stream));
+      rc = spb_ha_aggregate(semi, 65, mats_unwarp + 9 * n0, mats_fwd + 9 * n0, n, H, W, sums, accumulate || n0 > 0,
+                            base + o_agg, total - o_agg, stream);
+    }
     if (rc != SPB_OK) return rc;
   }
+  return SPB_OK;
+}
+
+int spb_net_profile(spb_net* h, int on) {
+  SPB_CHECK_ARG(h);
+  Net* net = reinterpret_cast<Net*>(h);
+  net->profile = on ? 1 : 0;
+  net->usedrecs = 0;
+  return SPB_OK;
+}
+
+int spb_net_profile_read(spb_net* h, float* ms, int* counts) {
+  SPB_CHECK_ARG(h && ms && counts);
+  Net* net = reinterpret_cast<Net*>(h);
+  for (int i = 0; i < kNumStages; ++i) {
+    ms[i] = 0.f;
+    counts[i] = 0;
+  }
+  for (int i = 0; i < net->usedrecs; ++i) {
+    ProfRec& r = net->recs[i];
+    SPB_CHECK_CUDA(cudaEventSynchronize(r.b));
+    float t = 0.f;
+    SPB_CHECK_CUDA(cudaEventElapsedTime(&t, r.a, r.b));
+    ms[r.stage] += t;
+    counts[r.stage]++;
+  }
+  net->usedrecs = 0;
   return SPB_OK;
 }
 

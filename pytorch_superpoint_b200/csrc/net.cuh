@@ -16,10 +16,20 @@ struct LayerDev {
   void* tmap_w;                // host copy of the CUtensorMap for w_tc (conv_tc.cu), 128 B
 };
 
+constexpr int kNumStages = 16;  // 0..11 layers, 12 warp, 13 aggregate
+
+struct ProfRec {
+  int stage;
+  cudaEvent_t a, b;
+};
+
 struct Net {
   LayerDev layer[kNumLayers];
   int impl;
   int ha_chunk;  // views per pass in spb_ha_heatmap_sums (0 = all)
+  int profile;   // record CUDA events around every stage launch (bench / roofline only)
+  ProfRec* recs;
+  int nrecs, caprecs, usedrecs;
 };
 
 // conv_simt.cu

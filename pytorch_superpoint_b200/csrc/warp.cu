@@ -19,6 +19,7 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 const char* last_error() { return g_err; }
+unsigned long long g_launches = 0;
 
 // One thread = 4 consecutive x of one (n, y).  MODE 0 bilinear, 1 nearest, 2 valid mask (no source).
 template <int MODE>
@@ -80,6 +81,7 @@ extern "C" {
 
 int spb_version(void) { return 100; }
 const char* spb_last_error_string(void) { return spb::last_error(); }
+unsigned long long spb_launch_count(void) { return __atomic_load_n(&spb::g_launches, __ATOMIC_RELAXED); }
 
 int spb_inv_warp_image_batch(const float* img, long long img_batch_stride, const float* mats, float* out, int N,
                              int H, int W, int mode, void* stream) {

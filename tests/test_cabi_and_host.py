@@ -1,0 +1,93 @@
+"""CPU-side tests: the C-ABI library loads and exports every symbol include/spb200.h declares (no compute
+calls), the ctypes prototypes cover the header, and the host logic (state-dict folding, sharding)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "spb200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(spb_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_header_symbol():
+    from pytorch_superpoint_b200.build import build
+    lib = ctypes.CDLL(build())
+    syms = _header_symbols()
+    assert len(syms) >= 24
+    for s in syms:
+        assert hasattr(lib, s), f"libspb200.so does not export {s}"
+    lib.spb_version.restype = ctypes.c_int
+    assert lib.spb_version() >= 100
+    lib.spb_nms_workspace_bytes.restype = ctypes.c_size_t
+    assert lib.spb_nms_workspace_bytes(1, 240, 320, 4) >= 48 * 64 * 8  # pure host arithmetic
+
+
+def test_ctypes_prototypes_cover_header():
+    from pytorch_superpoint_b200 import _lib
+    assert set(_header_symbols()) == set(_lib.PROTOTYPES)
+
+
+def test_ops_fail_loudly_without_cuda():
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    import pytorch_superpoint_b200 as pkg
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        pkg.inv_warp_image_batch(torch.zeros(1, 1, 8, 8), torch.eye(3)[None])
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        pkg.SuperPointNet_b200()(torch.zeros(1, 1, 8, 8))
+
+
+@pytest.mark.parametrize("layout", ["v1", "bnflat", "gauss2"])
+def test_fold_state_dict_matches_oracle(layout):
+    from oracle import oracle as O
+    from pytorch_superpoint_b200 import fold_state_dict
+    sd = O.synthetic_state_dict(layout, seed=3)
+    ws, bs = fold_state_dict(sd)
+    ref = O.fold_bn(O.canonical_params(sd))
+    for (name, *_), w, b in zip(O.LAYERS, ws, bs):
+        np.testing.assert_allclose(w, ref[name]["w"].numpy(), rtol=1e-6, atol=1e-7)
+        np.testing.assert_allclose(b, ref[name]["b"].numpy(), rtol=1e-6, atol=1e-7)
+    sd2 = {"module." + k: v for k, v in sd.items()}  # nn.DataParallel prefix
+    ws2, _ = fold_state_dict(sd2)
+    assert all(np.array_equal(a, b) for a, b in zip(ws, ws2))
+    with pytest.raises(KeyError):
+        fold_state_dict({"foo.weight": torch.zeros(1)})
+
+
+def test_net_state_dict_roundtrip():
+    from oracle import oracle as O
+    from pytorch_superpoint_b200 import SuperPointNet_b200
+    n = SuperPointNet_b200()
+    assert len(n.state_dict()) == 84  # gauss2 layout by default, like the reference's default model
+    sd = O.synthetic_state_dict("v1", seed=0)
+    n.load_state_dict(sd)
+    assert set(n.state_dict()) == set(sd)
+
+
+def test_shard_bounds():
+    from pytorch_superpoint_b200.sharding import shard_bounds
+    for n, w in [(100, 8), (100, 1), (20, 8), (5, 8), (100, 3)]:
+        spans = [shard_bounds(n, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        sizes = [b - a for a, b in spans]
+        assert max(sizes) - min(sizes) <= 1
+    assert [b - a for a, b in (shard_bounds(100, r, 8) for r in range(8))] == [13] * 4 + [12] * 4
+    with pytest.raises(ValueError):
+        shard_bounds(10, 8, 8)
+
+
+def test_synthetic_weights_match_oracle_generator():
+    from oracle import oracle as O
+    from pytorch_superpoint_b200.synthetic import synthetic_state_dict
+    for layout in ("v1", "bnflat", "gauss2"):
+        a, b = synthetic_state_dict(layout, 5), O.synthetic_state_dict(layout, 5)
+        assert list(a) == list(b) and all(torch.equal(a[k], b[k]) for k in a)

@@ -1,0 +1,106 @@
+"""GPU tests of the reference-facing front-end (SuperPointFrontend_b200), the sub-pixel step, the exporter
+and the .npz drop-in entry point."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import oracle as O  # noqa: E402  (checker only)
+
+
+def _fe(**kw):
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from pytorch_superpoint_b200.frontend import SuperPointFrontend_b200
+    fe = SuperPointFrontend_b200({"model": {"subpixel": {"enable": False}}}, "", 4, 0.015, 0.7, load=False, **kw)
+    return fe
+
+
+def test_nms_fast_generic_matches_reference_golden(golden):
+    g = golden("pts")
+    fe = _fe()
+    out, inds = fe.nms_fast(g["nms_in"], 64, 80, 3)
+    assert np.array_equal(out, g["nms_out"]) and np.array_equal(inds, g["nms_inds"])
+    e, ei = fe.nms_fast(np.zeros((3, 0)), 64, 80, 3)
+    assert e.shape == (3, 0) and ei.shape == (0,)
+    one, oi = fe.nms_fast(np.array([[3.4], [5.6], [0.9]]), 64, 80, 3)
+    assert np.array_equal(one, O.nms_fast(np.array([[3.4], [5.6], [0.9]]), 64, 80, 3)[0])
+
+
+def test_frontend_run_and_checkpoint_loading(tmp_path):
+    from pytorch_superpoint_b200.frontend import SuperPointFrontend_b200
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    sd = O.synthetic_state_dict("gauss2", seed=4)
+    tar = str(tmp_path / "superPointNet_100_checkpoint.pth.tar")
+    torch.save({"n_iter": 100, "model_state_dict": sd, "optimizer_state_dict": {}, "loss": 0.0}, tar)
+    fe = SuperPointFrontend_b200({"model": {"subpixel": {"enable": False}}}, tar, 4, 0.015, 0.7, device="cuda")
+    bare = str(tmp_path / "superpoint_v1.pth")
+    torch.save(O.synthetic_state_dict("v1", seed=4), bare)
+    SuperPointFrontend_b200({"model": {"subpixel": {"enable": False}}}, bare, 4, 0.015, 0.7, device="cuda")
+    x = torch.rand(2, 1, 64, 96, generator=torch.Generator().manual_seed(1))
+    heat = fe.run(x, onlyHeatmap=True, train=False)
+    assert tuple(heat.shape) == (2, 1, 64, 96) and heat.is_cuda
+    params = O.canonical_params(sd)
+    semi, desc = O.net_forward(params, x)
+    ref_heat = O.flatten_detection(semi.numpy())
+    assert np.abs(heat[:, 0].cpu().numpy() - ref_heat).max() < 1e-2
+    pts, pts_desc, dense, heat2 = fe.run(x, onlyHeatmap=False, train=False)
+    # NB the reference's own indexing (models/model_wrap.py:404) yields [256,K] per image, kept as is
+    assert len(pts) == 2 and pts[0].shape[0] == 3 and pts_desc[0].shape == (256, pts[0].shape[1])
+    assert tuple(dense.shape) == (2, 256, 64, 96)
+    # key-points bit-exact given OUR heat-map (the CPU oracle on the same fp32 array)
+    for b in range(2):
+        assert np.array_equal(pts[b], O.get_pts_from_heatmap(heat2[b, 0].cpu().numpy(), 0.015, 4))
+    # sparse descriptors at those points vs the oracle on the fp32 reference descriptors
+    d = fe.sample_desc_from_points(torch.from_numpy(desc.numpy()).cuda(), pts[0])
+    ref_d = O.sample_desc_from_points(desc.numpy(), pts[0])
+    assert np.abs(d - ref_d).max() < 1e-6
+
+
+def test_subpixel_vs_oracle():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from pytorch_superpoint_b200.subpixel import soft_argmax_points
+    rng = np.random.RandomState(0)
+    import cv2
+    heat = cv2.GaussianBlur(rng.rand(64, 80).astype(np.float32), (5, 5), 0) * 0.05
+    pts = O.get_pts_from_heatmap(heat, 0.015, 4, border_remove=0)  # includes points on the border (zero padding)
+    out = soft_argmax_points(torch.from_numpy(heat).cuda(), pts, 5)
+    ref = O.soft_argmax_points(heat, pts, 5)
+    assert out.shape == ref.shape and np.abs(out - ref).max() < 1e-4
+    assert np.abs(out[:2] - pts[:2]).max() < 2.0
+
+
+def test_export_entry_writes_reference_npz(tmp_path):
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from pytorch_superpoint_b200 import SuperPointNet_b200, make_ha_homographies
+    from pytorch_superpoint_b200.export import export_detector_homoAdapt_b200
+    sd = O.synthetic_state_dict("gauss2", seed=2)
+    net = SuperPointNet_b200()
+    net.load_state_dict(sd)
+    H, W, N = 64, 96, 8
+    rng = np.random.RandomState(3)
+    samples = []
+    for i in range(2):
+        mu, mf = make_ha_homographies(N, seed=20 + i)
+        samples.append({"image_2D": torch.from_numpy(rng.rand(1, 1, H, W).astype(np.float32)), "name": [f"img{i}"],
+                        "homographies": torch.from_numpy(mu)[None], "inv_homographies": torch.from_numpy(mf)[None]})
+    cfg = {"model": {"nms": 4, "top_k": 50, "detection_threshold": 0.015, "subpixel": {"enable": False}},
+           "data": {"export_folder": "train", "dataset": "Coco",
+                    "homography_adaptation": {"num": N, "homographies": {"params": {}}}}}
+    n = export_detector_homoAdapt_b200(cfg, str(tmp_path), loader=samples, net=net)
+    assert n == 2
+    for i, s in enumerate(samples):
+        f = np.load(os.path.join(str(tmp_path), "predictions", "train", f"img{i}.npz"))
+        pts = f["pts"]
+        assert pts.dtype == np.float64 and pts.shape[1] == 3 and pts.shape[0] <= 50
+        ref, agg = O.ha_export_one(s["image_2D"][0, 0].numpy(), s["homographies"][0].numpy(),
+                                   s["inv_homographies"][0].numpy(), O.canonical_params(sd), top_k=50, return_heat=True)
+        assert np.all(np.diff(pts[:, 2]) <= 0)
+    # resume: files exist -> nothing re-exported (export.py:302-306)
+    assert export_detector_homoAdapt_b200(cfg, str(tmp_path), loader=samples, net=net) == 0
