@@ -130,7 +130,7 @@ size_t spb_net_workspace_bytes(int B, int H, int W, int want_desc);
 int spb_net_forward(spb_net* net, const float* x, int B, int H, int W, float* semi, float* desc,
                     void* ws, size_t ws_bytes, void* stream);
 /* Debug/validation: run ONE layer (index 0..11) on NHWC bf16 input (fp32 [B,H,W] for layer 0);
- * output NHWC bf16 (fp32 for Pb/Db), 2x2 max-pool applied where the network has one. */
+ * output NHWC bf16 (fp32 for Pb/Db; Db rows L2-normalised), 2x2 max-pool applied where the network has one. */
 int spb_net_layer(spb_net* net, int layer, const void* in, void* out, int B, int H, int W, void* stream);
 
 /* ---- the whole HA step for one image (datasets/Coco.py:262-284 + export.py:309-310) -------------

@@ -66,6 +66,11 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -86,6 +91,29 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+template <int BW>
+__device__ __forceinline__ void tc_ld_nowait(uint32_t taddr, uint32_t (&v)[BW]);
+template <>
+__device__ __forceinline__ void tc_ld_nowait<16>(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+template <>
+__device__ __forceinline__ void tc_ld_nowait<32>(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 // K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
 // [0,14) start>>4, [16,30) LBO>>4 (unused for swizzled K-major), [32,46) SBO>>4, [46,48) version=1,
 // [61,64) layout (2 = SWIZZLE_128B).
@@ -101,9 +129,14 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
 // ------------------------------------------------------------------------------------------------
 // configuration
 // ------------------------------------------------------------------------------------------------
-template <int CIN_, int NPAD_, int KS_, bool HALO_, bool BRES_, int NA_, int NB_>
+// OUT_: 0 = ReLU + bf16 NHWC (encoder / head 3x3), 1 = raw fp32 rows staged through shared memory for coalesced
+// stores (convPb: 65 channels), 2 = fp32 rows L2-normalised over the channels (convDb).
+template <int CIN_, int NPAD_, int KS_, bool HALO_, bool BRES_, int NA_, int NB_, bool POOL_, int OUT_>
 struct ConvCfg {
-  static constexpr int CIN = CIN_, NPAD = NPAD_, KS = KS_, NA = NA_;
+  static constexpr int CIN = CIN_, NPAD = NPAD_, KS = KS_, NA = NA_, OUT = OUT_;
+  static constexpr bool POOL = POOL_;
+  static constexpr int BW = (NPAD_ % 32 == 0) ? 32 : 16;  // TMEM columns per epilogue batch
+  static constexpr int STAGE_BYTES = OUT_ == 1 ? 4 * 32 * 65 * 4 : 0;
   static constexpr bool HALO = HALO_ && KS_ > 1, BRES = BRES_;
   static constexpr int TAPS = KS * KS, CHUNKS = CIN / 64;
   static constexpr int TH = 16, TW = 8;
@@ -118,7 +151,7 @@ struct ConvCfg {
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
   static constexpr int NBAR = 2 * NA + 2 * NBS + 4;
   static constexpr size_t SMEM = 1024 /*align slack*/ + (size_t)NA * A_STRIDE + (size_t)NBS * B_BYTES + NPAD * 4 +
-                                 NBAR * 8 + 16;
+                                 NBAR * 8 + 16 + STAGE_BYTES;
   static_assert(B_BYTES % 1024 == 0, "weight block must keep 1024-byte alignment");
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
@@ -127,20 +160,20 @@ struct ConvArgs {
   const float* bias;
   void* out;
   int B, H, W, cout;
-  int relu, pool, out_f32, l2norm;
   int tiles_x, tiles_y, ntiles;
 };
 
 template <class C>
 __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act,
                                                          const __grid_constant__ CUtensorMap tm_wgt, ConvArgs a) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space
   uint8_t* sA = smem;
   uint8_t* sB = sA + (size_t)C::NA * C::A_STRIDE;
   float* sBias = reinterpret_cast<float*>(sB + (size_t)C::NBS * C::B_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + C::NPAD);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + C::NBAR);
+  float* sStage = reinterpret_cast<float*>(tmem_slot + 4);  // OUT == 1 only
   const uint32_t bar0 = smem_u32(bars);
   auto a_full = [&](int s) { return bar0 + 8u * s; };
   auto a_empty = [&](int s) { return bar0 + 8u * (C::NA + s); };
@@ -222,121 +255,210 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
     }
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(128, C::NPAD);
-      int sa = 0, pa = 0, sb = 0, pb = 0, as = 0, pacc = 0;
-      for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x) {
-        mbar_wait(acc_empty(as), pacc ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)as * C::ACC_STRIDE;
-        uint32_t accumulate = 0;
-        for (int kc = 0; kc < C::CHUNKS; ++kc) {
-          if (C::HALO) mbar_wait(a_full(sa), pa);
-          for (int tap = 0; tap < C::TAPS; ++tap) {
-            if (!C::HALO) mbar_wait(a_full(sa), pa);
-            const int slot = C::BRES ? kc * C::TAPS + tap : sb;
-            mbar_wait(b_full(slot), C::BRES ? 0 : pb);
-            tc_fence_after();
-            uint32_t a_addr = smem_u32(sA + (size_t)sa * C::A_STRIDE);
-            if (C::HALO) a_addr += ((tap / C::KS) * C::P + (tap % C::KS)) * 128;
-            const uint32_t b_addr = smem_u32(sB + (size_t)slot * C::B_BYTES);
+    // The whole warp walks the pipeline converged (barrier waits by every lane); one elected lane issues
+    // tcgen05.mma / tcgen05.commit.  Descriptors are a per-stage 64-bit base plus compile-time constants
+    // (tap shift, 32-byte K step), so the per-MMA issue cost is a couple of integer adds.
+    constexpr uint32_t idesc = make_idesc(128, C::NPAD);
+    constexpr uint64_t desc_hi_a = ((uint64_t)((C::P * 128) >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+    constexpr uint64_t desc_hi_b = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+    const uint32_t sA_u32 = smem_u32(sA), sB_u32 = smem_u32(sB);
+    int sa = 0, pa = 0, sb = 0, pb = 0, as = 0, pacc = 0;
+    bool first = true;
+    for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x) {
+      mbar_wait(acc_empty(as), pacc ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)as * C::ACC_STRIDE;
+#pragma unroll 1
+      for (int kc = 0; kc < C::CHUNKS; ++kc) {
+        if (C::HALO) mbar_wait(a_full(sa), pa);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              tc_mma(d_tmem, make_desc(a_addr + k * 32, C::P * 128), make_desc(b_addr + k * 32, 1024), idesc,
-                     accumulate);
-              accumulate = 1;
-            }
-            if (!C::BRES) {
-              tc_commit(b_empty(sb));
-              if (++sb == C::NBS) { sb = 0; pb ^= 1; }
-            }
-            if (!C::HALO) {
-              tc_commit(a_empty(sa));
-              if (++sa == C::NA) { sa = 0; pa ^= 1; }
-            }
+        for (int tap = 0; tap < C::TAPS; ++tap) {
+          if (!C::HALO) mbar_wait(a_full(sa), pa);
+          const int slot = C::BRES ? kc * C::TAPS + tap : sb;
+          if (C::BRES) {
+            if (first) mbar_wait(b_full(slot), 0);  // weights stay resident after the first tile
+          } else {
+            mbar_wait(b_full(slot), pb);
           }
-          if (C::HALO) {
-            tc_commit(a_empty(sa));
+          tc_fence_after();
+          const uint32_t tap_off = C::HALO ? ((tap / C::KS) * C::P + (tap % C::KS)) * 128 : 0;
+          const uint64_t adesc = desc_hi_a | (uint64_t)(((sA_u32 + (uint32_t)sa * C::A_STRIDE + tap_off) >> 4) | (1u << 16));
+          const uint64_t bdesc = desc_hi_b | (uint64_t)(((sB_u32 + (uint32_t)slot * C::B_BYTES) >> 4) | (1u << 16));
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              tc_mma(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                     (kc | tap | k) != 0 ? 1u : 0u);
+            if (!C::BRES) tc_commit(b_empty(sb));
+            if (!C::HALO) tc_commit(a_empty(sa));
+            if (C::HALO && tap == C::TAPS - 1) tc_commit(a_empty(sa));
+            if (kc == C::CHUNKS - 1 && tap == C::TAPS - 1) tc_commit(acc_full(as));
+          }
+          __syncwarp();
+          if (!C::BRES) {
+            if (++sb == C::NBS) { sb = 0; pb ^= 1; }
+          }
+          if (!C::HALO) {
             if (++sa == C::NA) { sa = 0; pa ^= 1; }
           }
         }
-        tc_commit(acc_full(as));
-        if (++as == 2) { as = 0; pacc ^= 1; }
+        if (C::HALO) {
+          if (++sa == C::NA) { sa = 0; pa ^= 1; }
+        }
       }
+      first = false;
+      if (++as == 2) { as = 0; pacc ^= 1; }
     }
   } else {
     // =========================== epilogue (warps 2..5) ===========================
+    // TMEM -> registers in batches of BW columns, software pipelined (the next batch's tcgen05.ld is in
+    // flight while this one is processed); the accumulator is handed back to the MMA warp as soon as the
+    // last batch has landed in registers.
     const int quad = warp & 3;  // TMEM lane quadrant this warp may read
     const int m = quad * 32 + lane, py = m >> 3, px = m & 7;
+    constexpr int BW = C::BW, NBATCH = C::NPAD / BW;
     int as = 0, pacc = 0;
     for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x) {
       const int n = t / (a.tiles_x * a.tiles_y), rem = t % (a.tiles_x * a.tiles_y);
-      const int y = (rem / a.tiles_x) * C::TH + py, x = (rem % a.tiles_x) * C::TW + px;
+      const int y0 = (rem / a.tiles_x) * C::TH, x0 = (rem % a.tiles_x) * C::TW;
+      const int y = y0 + py, x = x0 + px;
       mbar_wait(acc_full(as), pacc);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t)as * C::ACC_STRIDE + ((uint32_t)(quad * 32) << 16);
       bool valid = y < a.H && x < a.W;
       long long opix;
-      if (a.pool) {
+      if (C::POOL) {
         valid = valid && !(px & 1) && !(py & 1);
         opix = ((long long)n * (a.H >> 1) + (y >> 1)) * (a.W >> 1) + (x >> 1);
       } else {
         opix = ((long long)n * a.H + y) * a.W + x;
       }
-      float inv_norm = 1.f;
-      if (a.l2norm) {
+      float norm = 1.f;
+      if (C::OUT == 2) {  // first pass over the accumulator: squared norm of the 256-channel row
         float ss = 0.f;
         for (int c0 = 0; c0 < C::NPAD; c0 += 16) {
           uint32_t v[16];
-          tc_ld16(taddr + c0, v);
+          tc_ld_nowait<16>(taddr + c0, v);
+          tc_wait_ld();
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const float f = __uint_as_float(v[j]) + sBias[c0 + j];
             ss = fmaf(f, f, ss);
           }
         }
-        inv_norm = sqrtf(ss);
+        norm = sqrtf(ss);
       }
-      for (int c0 = 0; c0 < C::NPAD; c0 += 16) {
-        uint32_t v[16];
-        tc_ld16(taddr + c0, v);
-        float f[16];
+      if (C::OUT == 3) {
+        // convPb in the HA path: 65-way softmax of the cell in registers (each thread holds its whole row),
+        // dustbin dropped, probabilities written as [.,64] fp32 -- utils/utils.py:514-523 fused here.
+        uint32_t w[80];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          f[j] = __uint_as_float(v[j]) + sBias[c0 + j];
-          if (a.relu) f[j] = fmaxf(f[j], 0.f);
-          if (a.pool) {
-            f[j] = fmaxf(f[j], __shfl_xor_sync(0xffffffffu, f[j], 1));
-            f[j] = fmaxf(f[j], __shfl_xor_sync(0xffffffffu, f[j], 8));
-          }
-          if (a.l2norm) f[j] = __fdiv_rn(f[j], inv_norm);
+        for (int b = 0; b < 5; ++b) tc_ld_nowait<16>(taddr + b * 16, *reinterpret_cast<uint32_t(*)[16]>(&w[b * 16]));
+        tc_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty(as));
+        float mx = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 65; ++j) {
+          const float f = __uint_as_float(w[j]) + sBias[j];
+          w[j] = __float_as_uint(f);
+          mx = fmaxf(mx, f);
+        }
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < 65; ++j) {
+          const float e = expf(__uint_as_float(w[j]) - mx);
+          w[j] = __float_as_uint(e);
+          sum += e;
         }
         if (valid) {
-          if (a.out_f32) {
-            float* o = static_cast<float*>(a.out) + opix * a.cout + c0;
-            if (c0 + 16 <= a.cout && (a.cout & 3) == 0) {
+          float* o = static_cast<float*>(a.out) + opix * 64;
 #pragma unroll
-              for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-            } else {
-              for (int j = 0; j < 16; ++j)
-                if (c0 + j < a.cout) o[j] = f[j];
+          for (int j = 0; j < 64; j += 4)
+            *reinterpret_cast<float4*>(o + j) =
+                make_float4(__fdiv_rn(__uint_as_float(w[j]), sum), __fdiv_rn(__uint_as_float(w[j + 1]), sum),
+                            __fdiv_rn(__uint_as_float(w[j + 2]), sum), __fdiv_rn(__uint_as_float(w[j + 3]), sum));
+        }
+        if (++as == 2) { as = 0; pacc ^= 1; }
+        continue;
+      }
+      uint32_t v[2][BW];
+      tc_ld_nowait<BW>(taddr, v[0]);
+#pragma unroll
+      for (int b = 0; b < NBATCH; ++b) {
+        tc_wait_ld();
+        if (b + 1 < NBATCH) {
+          tc_ld_nowait<BW>(taddr + (b + 1) * BW, v[(b + 1) & 1]);
+        } else {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(acc_empty(as));
+        }
+        const int c0 = b * BW;
+        float f[BW];
+#pragma unroll
+        for (int j = 0; j < BW; j += 4) {
+          const float4 bb = *reinterpret_cast<const float4*>(sBias + c0 + j);
+          f[j] = __uint_as_float(v[b & 1][j]) + bb.x;
+          f[j + 1] = __uint_as_float(v[b & 1][j + 1]) + bb.y;
+          f[j + 2] = __uint_as_float(v[b & 1][j + 2]) + bb.z;
+          f[j + 3] = __uint_as_float(v[b & 1][j + 3]) + bb.w;
+        }
+        if (C::OUT == 0) {
+#pragma unroll
+          for (int j = 0; j < BW; ++j) {
+            f[j] = fmaxf(f[j], 0.f);
+            if (C::POOL) {
+              f[j] = fmaxf(f[j], __shfl_xor_sync(0xffffffffu, f[j], 1));
+              f[j] = fmaxf(f[j], __shfl_xor_sync(0xffffffffu, f[j], 8));
             }
-          } else {
+          }
+          if (valid) {
             __nv_bfloat16* o = static_cast<__nv_bfloat16*>(a.out) + opix * a.cout + c0;
-            uint32_t pk[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-              pk[j] = *reinterpret_cast<const uint32_t*>(&h);
+            for (int j = 0; j < BW; j += 8) {
+              uint32_t pk[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const __nv_bfloat162 h = __floats2bfloat162_rn(f[j + 2 * q], f[j + 2 * q + 1]);
+                pk[q] = *reinterpret_cast<const uint32_t*>(&h);
+              }
+              *reinterpret_cast<uint4*>(o + j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             }
-            *reinterpret_cast<uint4*>(o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            *reinterpret_cast<uint4*>(o + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          }
+        } else if (C::OUT == 1) {
+          // stage the warp's 32 pixels x cout floats exactly as they lie in global memory (row stride = cout)
+          float* st = sStage + quad * (32 * 65) + lane * a.cout + c0;
+#pragma unroll
+          for (int j = 0; j < BW; ++j)
+            if (c0 + j < a.cout) st[j] = f[j];
+        } else {
+          if (valid) {
+            float* o = static_cast<float*>(a.out) + opix * a.cout + c0;
+#pragma unroll
+            for (int j = 0; j < BW; j += 4)
+              *reinterpret_cast<float4*>(o + j) = make_float4(__fdiv_rn(f[j], norm), __fdiv_rn(f[j + 1], norm),
+                                                              __fdiv_rn(f[j + 2], norm), __fdiv_rn(f[j + 3], norm));
           }
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(acc_empty(as));
+      if (C::OUT == 1) {
+        // coalesced copy-out: the warp owns 4 image rows x 8 pixels; each row's 8*cout floats are contiguous
+        __syncwarp();
+        const int seg = 8 * a.cout;
+#pragma unroll 1
+        for (int r = 0; r < 4; ++r) {
+          const int yy = y0 + quad * 4 + r;
+          if (yy < a.H && x0 < a.W) {
+            float* o = static_cast<float*>(a.out) + (((long long)n * a.H + yy) * a.W + x0) * a.cout;
+            const float* src = sStage + quad * (32 * 65) + r * seg;
+            const int lim = min(seg, (a.W - x0) * a.cout);
+            for (int i = lane; i < lim; i += 32) o[i] = src[i];
+          }
+        }
+        __syncwarp();
+      }
       if (++as == 2) { as = 0; pacc ^= 1; }
     }
   }
@@ -428,7 +550,7 @@ extern "C" int spb_conv_tc_set_halo(int on) {
 }
 
 template <class C>
-static int launch(const LayerDev& L, const __nv_bfloat16* in, void* out, int B, int H, int W, int out_f32, int l2norm,
+static int launch(const LayerDev& L, const __nv_bfloat16* in, void* out, int B, int H, int W, int out_mode,
                   cudaStream_t st) {
   CUtensorMap tm_act, tm_wgt;
   memcpy(&tm_wgt, L.tmap_w, sizeof(tm_wgt));
@@ -441,10 +563,12 @@ static int launch(const LayerDev& L, const __nv_bfloat16* in, void* out, int B, 
   a.H = H;
   a.W = W;
   a.cout = L.cout;
-  a.relu = L.relu;
-  a.pool = L.pool;
-  a.out_f32 = out_f32;
-  a.l2norm = l2norm;
+  if (L.pool != (C::POOL ? 1 : 0) || L.relu != (C::OUT == 0 ? 1 : 0) || out_mode != C::OUT ||
+      ((C::OUT == 1 || C::OUT == 3) && L.cout != 65)) {
+    set_error("conv_tc: kernel configuration does not match the layer (pool %d relu %d out_mode %d)", L.pool, L.relu,
+              out_mode);
+    return SPB_EINVAL;
+  }
   a.tiles_x = ceil_div(W, C::TW);
   a.tiles_y = ceil_div(H, C::TH);
   a.ntiles = B * a.tiles_x * a.tiles_y;
@@ -455,7 +579,7 @@ static int launch(const LayerDev& L, const __nv_bfloat16* in, void* out, int B, 
   return SPB_OK;
 }
 
-int conv_tc(const LayerDev& L, const __nv_bfloat16* in, void* out, int B, int H, int W, int out_f32, int l2norm,
+int conv_tc(const LayerDev& L, const __nv_bfloat16* in, void* out, int B, int H, int W, int out_mode,
             cudaStream_t st) {
   if (!L.tmap_w) {
     set_error("conv_tc: layer has no weight tensor map");
@@ -466,23 +590,24 @@ int conv_tc(const LayerDev& L, const __nv_bfloat16* in, void* out, int B, int H,
     return SPB_EINVAL;
   }
   const bool halo = g_halo_mode != 0;
-  //                                   CIN NPAD KS HALO  BRES  NA NB
-  if (L.ks == 3 && L.cin == 64 && L.cout_pad == 64)
-    return halo ? launch<ConvCfg<64, 64, 3, true, true, 4, 0>>(L, in, out, B, H, W, out_f32, l2norm, st)
-                : launch<ConvCfg<64, 64, 3, false, true, 6, 0>>(L, in, out, B, H, W, out_f32, l2norm, st);
+#define SPB_CONV(CIN, NPAD, KS, HALO, BRES, NA, NB, POOL, OUT) \
+  launch<ConvCfg<CIN, NPAD, KS, HALO, BRES, NA, NB, POOL, OUT>>(L, in, out, B, H, W, out_mode, st)
+  if (L.ks == 3 && L.cin == 64 && L.cout_pad == 64) {
+    if (L.pool) return halo ? SPB_CONV(64, 64, 3, true, true, 4, 0, true, 0) : SPB_CONV(64, 64, 3, false, true, 6, 0, true, 0);
+    return halo ? SPB_CONV(64, 64, 3, true, true, 4, 0, false, 0) : SPB_CONV(64, 64, 3, false, true, 6, 0, false, 0);
+  }
   if (L.ks == 3 && L.cin == 64 && L.cout_pad == 128)
-    return halo ? launch<ConvCfg<64, 128, 3, true, true, 3, 0>>(L, in, out, B, H, W, out_f32, l2norm, st)
-                : launch<ConvCfg<64, 128, 3, false, true, 4, 0>>(L, in, out, B, H, W, out_f32, l2norm, st);
-  if (L.ks == 3 && L.cin == 128 && L.cout_pad == 128)
-    return halo ? launch<ConvCfg<128, 128, 3, true, false, 4, 6>>(L, in, out, B, H, W, out_f32, l2norm, st)
-                : launch<ConvCfg<128, 128, 3, false, false, 6, 6>>(L, in, out, B, H, W, out_f32, l2norm, st);
+    return halo ? SPB_CONV(64, 128, 3, true, true, 3, 0, false, 0) : SPB_CONV(64, 128, 3, false, true, 4, 0, false, 0);
+  if (L.ks == 3 && L.cin == 128 && L.cout_pad == 128) {
+    if (L.pool) return halo ? SPB_CONV(128, 128, 3, true, false, 4, 6, true, 0) : SPB_CONV(128, 128, 3, false, false, 6, 6, true, 0);
+    return halo ? SPB_CONV(128, 128, 3, true, false, 4, 6, false, 0) : SPB_CONV(128, 128, 3, false, false, 6, 6, false, 0);
+  }
   if (L.ks == 3 && L.cin == 128 && L.cout_pad == 256)
-    return halo ? launch<ConvCfg<128, 256, 3, true, false, 3, 4>>(L, in, out, B, H, W, out_f32, l2norm, st)
-                : launch<ConvCfg<128, 256, 3, false, false, 4, 4>>(L, in, out, B, H, W, out_f32, l2norm, st);
-  if (L.ks == 1 && L.cin == 256 && L.cout_pad == 80)
-    return launch<ConvCfg<256, 80, 1, false, true, 6, 0>>(L, in, out, B, H, W, out_f32, l2norm, st);
-  if (L.ks == 1 && L.cin == 256 && L.cout_pad == 256)
-    return launch<ConvCfg<256, 256, 1, false, true, 4, 0>>(L, in, out, B, H, W, out_f32, l2norm, st);
+    return halo ? SPB_CONV(128, 256, 3, true, false, 3, 4, false, 0) : SPB_CONV(128, 256, 3, false, false, 4, 4, false, 0);
+  if (L.ks == 1 && L.cin == 256 && L.cout_pad == 80 && out_mode == 1) return SPB_CONV(256, 80, 1, false, true, 6, 0, false, 1);
+  if (L.ks == 1 && L.cin == 256 && L.cout_pad == 80 && out_mode == 3) return SPB_CONV(256, 80, 1, false, true, 6, 0, false, 3);
+  if (L.ks == 1 && L.cin == 256 && L.cout_pad == 256 && out_mode == 2) return SPB_CONV(256, 256, 1, false, true, 4, 0, false, 2);
+#undef SPB_CONV
   set_error("conv_tc: unsupported layer shape ks=%d cin=%d cout_pad=%d", L.ks, L.cin, L.cout_pad);
   return SPB_EINVAL;
 }

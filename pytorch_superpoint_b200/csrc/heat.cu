@@ -222,6 +222,46 @@ __global__ void __launch_bounds__(256) ha_aggregate_kernel(AggParams p) {
   }
 }
 
+// HA product path: the detector head's epilogue already wrote softmax probabilities (dustbin dropped) as
+// probs[N,Hc,Wc,64] and the warp kernel wrote the valid-mask bits, so aggregation is a pure gather:
+// one thread per output pixel, views n = g, g+G, ... accumulated in registers in a fixed order.
+__global__ void __launch_bounds__(256) agg_probs_kernel(const float* __restrict__ probs,
+                                                        const uint8_t* __restrict__ bits,
+                                                        const float* __restrict__ mu, int N, int H, int W, int G,
+                                                        float* __restrict__ part, Lin lx, Lin ly) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= W || y >= H) return;
+  const int Wc = W >> 3, Hc = H >> 3;
+  const float u = lx.at(x), v = ly.at(y);
+  float num = 0.f, den = 0.f;
+  for (int n = blockIdx.z; n < N; n += G) {
+    const Mat3 M = load_mat(mu + 9 * n);
+    float ix, iy;
+    warp_coord(M, u, v, W, H, ix, iy);
+    const Taps tp = make_taps(ix, iy);
+    const float* pn = probs + (long long)n * Hc * Wc * 64;
+    const uint8_t* bn = bits + (long long)n * H * Wc;
+    float a = 0.f, b = 0.f;
+    auto tap = [&](float xf, float yf, float w) {
+      if (!in_bounds(xf, yf, W, H)) return;
+      const int xx = (int)xf, yy = (int)yf;
+      const float m = (float)((__ldg(bn + yy * Wc + (xx >> 3)) >> (xx & 7)) & 1);
+      const float pr = __ldg(pn + ((yy >> 3) * Wc + (xx >> 3)) * 64 + ((yy & 7) << 3 | (xx & 7)));
+      a = __fadd_rn(a, __fmul_rn(__fmul_rn(pr, m), w));
+      b = __fadd_rn(b, __fmul_rn(m, w));
+    };
+    tap(tp.x0, tp.y0, tp.w_nw);
+    tap(tp.x1, tp.y0, tp.w_ne);
+    tap(tp.x0, tp.y1, tp.w_sw);
+    tap(tp.x1, tp.y1, tp.w_se);
+    num = __fadd_rn(num, a);
+    den = __fadd_rn(den, b);
+  }
+  float* o = part + (long long)blockIdx.z * 2 * H * W + (long long)y * W + x;
+  o[0] = num;
+  o[(long long)H * W] = den;
+}
+
 __global__ void __launch_bounds__(256) agg_reduce_kernel(const float* __restrict__ part, int G, long long n,
                                                          float* __restrict__ sums, int accumulate) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -243,6 +283,23 @@ static int agg_groups(int N, int H, int W) {
   if (G > N) G = N;
   if (G < 1) G = 1;
   return G;
+}
+
+int aggregate_probs(const float* probs, const uint8_t* bits, const float* mats_unwarp, int N, int H, int W,
+                    float* sums, int accumulate, void* ws, cudaStream_t st) {
+  const int tiles = ceil_div(W, 32) * ceil_div(H, 8);
+  int G = ceil_div(4LL * kNumSMs * 8, tiles);
+  if (G > N) G = N;
+  if (G > agg_groups(N, H, W)) G = agg_groups(N, H, W);  // never exceed the workspace sized by the public call
+  if (G < 1) G = 1;
+  float* part = static_cast<float*>(ws);
+  dim3 grid(ceil_div(W, 32), ceil_div(H, 8), G);
+  agg_probs_kernel<<<grid, 256, 0, st>>>(probs, bits, mats_unwarp, N, H, W, G, part, Lin(W), Lin(H));
+  SPB_CHECK_LAUNCH();
+  const long long n = 2LL * H * W;
+  agg_reduce_kernel<<<min(ceil_div(n, 256), kNumSMs * 8), 256, 0, st>>>(part, G, n, sums, accumulate);
+  SPB_CHECK_LAUNCH();
+  return SPB_OK;
 }
 
 }  // namespace spb

@@ -64,37 +64,70 @@ struct StageTimer {
   }
 };
 
-static int run_layer(const Net* net, int li, const void* in, void* out, int B, int H, int W, int out_f32, int l2norm,
+// out_mode: 0 bf16 NHWC, 1 fp32 rows, 2 fp32 L2-normalised rows, 3 softmax probabilities [.,64] (convPb)
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ semi, float* __restrict__ probs,
+                                                           long long rows) {
+  const int lane = threadIdx.x & 31;
+  for (long long r = blockIdx.x * 8LL + (threadIdx.x >> 5); r < rows; r += gridDim.x * 8LL) {
+    const float* p = semi + r * 65;
+    const float a = p[lane], b = p[lane + 32], d = (lane == 0) ? p[64] : -INFINITY;
+    const float mx = warp_max(fmaxf(fmaxf(a, b), d));
+    const float ea = expf(a - mx), eb = expf(b - mx), ed = (lane == 0) ? expf(d - mx) : 0.f;
+    const float s = warp_sum(ea + eb + ed);
+    probs[r * 64 + lane] = __fdiv_rn(ea, s);
+    probs[r * 64 + lane + 32] = __fdiv_rn(eb, s);
+  }
+}
+
+static int run_layer(const Net* net, int li, const void* in, void* out, int B, int H, int W, int out_mode,
                      cudaStream_t st) {
   const LayerDev& L = net->layer[li];
   StageTimer tm(net, li, st);
   if (li == 0) return conv1a_simt(L, static_cast<const float*>(in), static_cast<__nv_bfloat16*>(out), B, H, W, st);
   if (net->impl == SPB_IMPL_TCGEN05)
-    return conv_tc(L, static_cast<const __nv_bfloat16*>(in), out, B, H, W, out_f32, l2norm, st);
-  int rc = conv_simt(L, static_cast<const __nv_bfloat16*>(in), out, B, H, W, out_f32, st);
-  if (rc == SPB_OK && l2norm) rc = l2norm_rows(static_cast<float*>(out), (long long)B * H * W, L.cout, st);
+    return conv_tc(L, static_cast<const __nv_bfloat16*>(in), out, B, H, W, out_mode, st);
+  if (out_mode == 3) {
+    set_error("run_layer: softmax output is produced by forward() in SIMT mode");
+    return SPB_EINVAL;
+  }
+  int rc = conv_simt(L, static_cast<const __nv_bfloat16*>(in), out, B, H, W, out_mode != 0, st);
+  if (rc == SPB_OK && out_mode == 2) rc = l2norm_rows(static_cast<float*>(out), (long long)B * H * W, L.cout, st);
   return rc;
 }
 
-static int forward(const Net* net, const float* x, int B, int H, int W, float* semi, float* desc, void* ws,
-                   cudaStream_t st) {
+// semi: logits [B,Hc,Wc,65] (or NULL); probs: softmax probabilities [B,Hc,Wc,64] (or NULL); desc optional
+static int forward(const Net* net, const float* x, int B, int H, int W, float* semi, float* probs, float* desc,
+                   void* ws, cudaStream_t st) {
   Workspace w(ws, B, H, W);
   int rc;
-#define RUN(li, in, out, h, wd, f32, l2)                                     \
-  if ((rc = run_layer(net, li, in, out, B, h, wd, f32, l2, st)) != SPB_OK) return rc
-  RUN(0, x, w.buf0, H, W, 0, 0);
-  RUN(1, w.buf0, w.buf1, H, W, 0, 0);  // + pool -> H/2
-  RUN(2, w.buf1, w.buf0, H / 2, W / 2, 0, 0);
-  RUN(3, w.buf0, w.buf1, H / 2, W / 2, 0, 0);  // + pool -> H/4
-  RUN(4, w.buf1, w.buf0, H / 4, W / 4, 0, 0);
-  RUN(5, w.buf0, w.buf1, H / 4, W / 4, 0, 0);  // + pool -> H/8
-  RUN(6, w.buf1, w.buf0, H / 8, W / 8, 0, 0);
-  RUN(7, w.buf0, w.buf1, H / 8, W / 8, 0, 0);
-  RUN(8, w.buf1, w.buf0, H / 8, W / 8, 0, 0);
-  RUN(9, w.buf0, semi, H / 8, W / 8, 1, 0);
+#define RUN(li, in, out, h, wd, mode)                                     \
+  if ((rc = run_layer(net, li, in, out, B, h, wd, mode, st)) != SPB_OK) return rc
+  RUN(0, x, w.buf0, H, W, 0);
+  RUN(1, w.buf0, w.buf1, H, W, 0);  // + pool -> H/2
+  RUN(2, w.buf1, w.buf0, H / 2, W / 2, 0);
+  RUN(3, w.buf0, w.buf1, H / 2, W / 2, 0);  // + pool -> H/4
+  RUN(4, w.buf1, w.buf0, H / 4, W / 4, 0);
+  RUN(5, w.buf0, w.buf1, H / 4, W / 4, 0);  // + pool -> H/8
+  RUN(6, w.buf1, w.buf0, H / 8, W / 8, 0);
+  RUN(7, w.buf0, w.buf1, H / 8, W / 8, 0);
+  RUN(8, w.buf1, w.buf0, H / 8, W / 8, 0);
+  if (semi) RUN(9, w.buf0, semi, H / 8, W / 8, 1);
+  if (probs) {
+    if (net->impl == SPB_IMPL_TCGEN05) {
+      RUN(9, w.buf0, probs, H / 8, W / 8, 3);
+    } else {  // validation path: logits (semi) first, then a softmax kernel
+      if (!semi) {
+        set_error("forward: the SIMT validation path needs a semi buffer to produce probabilities");
+        return SPB_EINVAL;
+      }
+      const long long rows = (long long)B * (H / 8) * (W / 8);
+      softmax_rows_kernel<<<min(ceil_div(rows, 8), kNumSMs * 8), 256, 0, st>>>(semi, probs, rows);
+      SPB_CHECK_LAUNCH();
+    }
+  }
   if (desc) {
-    RUN(10, w.buf1, w.buf0, H / 8, W / 8, 0, 0);
-    RUN(11, w.buf0, desc, H / 8, W / 8, 1, 1);
+    RUN(10, w.buf1, w.buf0, H / 8, W / 8, 0);
+    RUN(11, w.buf0, desc, H / 8, W / 8, 2);
   }
 #undef RUN
   return SPB_OK;
@@ -206,13 +239,13 @@ int spb_net_forward(spb_net* h, const float* x, int B, int H, int W, float* semi
     set_error("spb_net_forward: workspace %zu < %zu bytes", ws_bytes, spb_net_workspace_bytes(B, H, W, desc != nullptr));
     return SPB_ENOMEM;
   }
-  return forward(reinterpret_cast<Net*>(h), x, B, H, W, semi, desc, align_ptr(ws), as_stream(stream));
+  return forward(reinterpret_cast<Net*>(h), x, B, H, W, semi, nullptr, desc, align_ptr(ws), as_stream(stream));
 }
 
 int spb_net_layer(spb_net* h, int layer, const void* in, void* out, int B, int H, int W, void* stream) {
   SPB_CHECK_ARG(h && in && out && layer >= 0 && layer < kNumLayers && B >= 1 && H >= 1 && W >= 1);
-  const int f32 = (layer == 9 || layer == 11);
-  return run_layer(reinterpret_cast<Net*>(h), layer, in, out, B, H, W, f32, 0, as_stream(stream));
+  const int mode = layer == 9 ? 1 : (layer == 11 ? 2 : 0);
+  return run_layer(reinterpret_cast<Net*>(h), layer, in, out, B, H, W, mode, as_stream(stream));
 }
 
 // ---- whole HA step ----------------------------------------------------------------------------------
@@ -221,8 +254,10 @@ static void ha_layout(int n, int H, int W, size_t& off_warp, size_t& off_semi, s
   size_t o = 0;
   off_warp = o;
   o += align_up((size_t)n * H * W * 4, 1024);
+  o += align_up((size_t)n * H * (W / 8), 1024);  // valid-mask bits follow the warped views
   off_semi = o;
-  o += align_up((size_t)n * (H / 8) * (W / 8) * 65 * 4, 1024);
+  o += align_up((size_t)n * (H / 8) * (W / 8) * 65 * 4, 1024);  // probabilities [.,64] (or logits [.,65] in SIMT mode)
+  o += align_up((size_t)n * (H / 8) * (W / 8) * 64 * 4, 1024);
   off_agg = o;
   o += align_up(spb_ha_aggregate_workspace_bytes(n, H, W), 1024);
   off_net = o;
@@ -251,21 +286,26 @@ int spb_ha_heatmap_sums(spb_net* h, const float* img, const float* mats_unwarp, 
   }
   char* base = static_cast<char*>(align_ptr(ws));
   float* warped = reinterpret_cast<float*>(base + o_warp);
+  uint8_t* bits = reinterpret_cast<uint8_t*>(base + o_warp + align_up((size_t)chunk * H * W * 4, 1024));
   float* semi = reinterpret_cast<float*>(base + o_semi);
+  float* probs = reinterpret_cast<float*>(base + o_semi + align_up((size_t)chunk * (H / 8) * (W / 8) * 65 * 4, 1024));
+  const bool tc = net->impl == SPB_IMPL_TCGEN05;
   for (int n0 = 0; n0 < N; n0 += chunk) {
     const int n = (N - n0 < chunk) ? N - n0 : chunk;
     int rc;
     {
       StageTimer tm(net, 12, as_stream(stream));
-      rc = spb_inv_warp_image_batch(img, 0, mats_fwd + 9 * n0, warped, n, H, W, SPB_MODE_BILINEAR, stream);
+      rc = warp_with_mask_bits(img, mats_fwd + 9 * n0, warped, bits, n, H, W, as_stream(stream));
     }
     if (rc != SPB_OK) return rc;
-    rc = forward(net, warped, n, H, W, semi, nullptr, base + o_net, as_stream(stream));
+    // the detector head writes softmax probabilities directly (tcgen05 epilogue); the validation path goes
+    // through logits + a softmax kernel
+    rc = forward(net, warped, n, H, W, tc ? nullptr : semi, probs, nullptr, base + o_net, as_stream(stream));
     if (rc != SPB_OK) return rc;
     {
       StageTimer tm(net, 13, as_stream(stream));
-      rc = spb_ha_aggregate(semi, 65, mats_unwarp + 9 * n0, mats_fwd + 9 * n0, n, H, W, sums, accumulate || n0 > 0,
-                            base + o_agg, total - o_agg, stream);
+      rc = aggregate_probs(probs, bits, mats_unwarp + 9 * n0, n, H, W, sums, accumulate || n0 > 0, base + o_agg,
+                           as_stream(stream));
     }
     if (rc != SPB_OK) return rc;
   }

@@ -37,9 +37,16 @@ int conv1a_simt(const LayerDev& L, const float* x, __nv_bfloat16* out, int B, in
 int conv_simt(const LayerDev& L, const __nv_bfloat16* in, void* out, int B, int H, int W, int out_f32, cudaStream_t st);
 int l2norm_rows(float* d, long long rows, int C, cudaStream_t st);
 
+// warp.cu / heat.cu pieces used by the fused HA path
+int warp_with_mask_bits(const float* img, const float* mats, float* out, uint8_t* bits, int N, int H, int W,
+                        cudaStream_t st);
+int aggregate_probs(const float* probs, const uint8_t* bits, const float* mats_unwarp, int N, int H, int W,
+                    float* sums, int accumulate, void* ws, cudaStream_t st);
+
 // conv_tc.cu (tcgen05 / TMEM / TMA)
 int conv_tc_prepare(LayerDev& L);  // builds the weight tensor map after w_tc is uploaded
-int conv_tc(const LayerDev& L, const __nv_bfloat16* in, void* out, int B, int H, int W, int out_f32, int l2norm,
-            cudaStream_t st);
+// out_mode: 0 bf16 NHWC, 1 fp32 rows (cout channels), 2 fp32 rows L2-normalised, 3 softmax probabilities
+// (convPb only: fp32 [.,64], dustbin dropped)
+int conv_tc(const LayerDev& L, const __nv_bfloat16* in, void* out, int B, int H, int W, int out_mode, cudaStream_t st);
 
 }  // namespace spb

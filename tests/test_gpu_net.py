@@ -51,6 +51,8 @@ def _ref_layer(li, x_nhwc, params):
         y = torch.relu(y)
     if O.LAYERS[li][5]:
         y = torch.nn.functional.max_pool2d(y, 2, 2)
+    if li == 11:  # convDb rows come back L2-normalised (models/SuperPointNet_pretrained.py:73-74)
+        y = y / torch.norm(y, p=2, dim=1, keepdim=True)
     return y.permute(0, 2, 3, 1).contiguous()
 
 
