@@ -473,6 +473,181 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
 }
 
 // ------------------------------------------------------------------------------------------------
+// conv1a (1 -> 64, 3x3) on the tensor cores: 128 consecutive pixels per tile, the 9 taps of every pixel are
+// gathered straight from the fp32 image into a K=16 im2col row (bf16, no-swizzle K-major core matrices:
+// 8 rows x 16 B, K chunks LBO = 128 B apart, 8-row groups SBO = 256 B apart), ONE tcgen05.mma (M128 N64 K16)
+// per tile, epilogue bias + ReLU + bf16 and a fully contiguous 16 KB NHWC store.  HBM-write bound.
+// Warps 0..3: im2col build of tile i+1, then epilogue of tile i (double-buffered A and TMEM); warp 4: MMA.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t make_desc_noswz(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | ((uint64_t)1 << 46);
+}
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0),
+               "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+struct Conv1aSmem {
+  uint8_t stage[2][16384];  // output tiles, 128 rows x 128 B, SWIZZLE_128B (TMA store source)
+  uint8_t a[2][4096];       // im2col tiles
+  uint8_t b[2048];          // weights [64][16] in core-matrix layout
+  float bias[64];
+  uint64_t bars[6];         // a_full[2], acc_full[2], acc_empty[2]
+  uint32_t tmem_slot;
+};
+
+__global__ void __launch_bounds__(160, 4) conv1a_tc_kernel(const __grid_constant__ CUtensorMap tm_out,
+                                                           const float* __restrict__ x,
+                                                           const __nv_bfloat16* __restrict__ w16,
+                                                           const float* __restrict__ bias, long long npix, int H, int W,
+                                                           int ntiles) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  Conv1aSmem& sm = *reinterpret_cast<Conv1aSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar0 = smem_u32(sm.bars);
+  auto a_full = [&](int s) { return bar0 + 8u * s; };
+  auto acc_full = [&](int s) { return bar0 + 8u * (2 + s); };
+  auto acc_empty = [&](int s) { return bar0 + 8u * (4 + s); };
+
+  if (threadIdx.x < 64) {
+    sm.bias[threadIdx.x] = bias[threadIdx.x];
+    const uint4* src = reinterpret_cast<const uint4*>(w16 + threadIdx.x * 16);  // weight row n: two 16-byte K chunks
+    const int n = threadIdx.x;
+    *reinterpret_cast<uint4*>(sm.b + (n >> 3) * 256 + (n & 7) * 16) = src[0];
+    *reinterpret_cast<uint4*>(sm.b + (n >> 3) * 256 + 128 + (n & 7) * 16) = src[1];
+  }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(a_full(s), 128);
+      mbar_init(acc_full(s), 1);
+      mbar_init(acc_empty(s), 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_slot)),
+                 "r"(128u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // sm.b written by the generic proxy, read by UMMA
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = sm.tmem_slot;
+
+  if (warp == 4) {
+    constexpr uint32_t idesc = make_idesc(128, 64);
+    const uint64_t bdesc = make_desc_noswz(smem_u32(sm.b), 128, 256);
+    int it = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+      const int buf = it & 1, ph = (it >> 1) & 1;
+      mbar_wait(acc_empty(buf), ph ^ 1);
+      mbar_wait(a_full(buf), ph);
+      tc_fence_after();
+      if (elect_one()) {
+        tc_mma(tmem_base + buf * 64, make_desc_noswz(smem_u32(sm.a[buf]), 128, 256), bdesc, idesc, 0u);
+        tc_commit(acc_full(buf));
+      }
+      __syncwarp();
+    }
+  } else {
+    const int r = threadIdx.x;  // im2col row / TMEM lane / output row of this thread
+    auto build = [&](int t, int buf) {
+      const long long p = (long long)t * 128 + r;
+      uint32_t pk[5] = {0, 0, 0, 0, 0};
+      if (p < npix) {
+        const int px = (int)(p % W), py = (int)((p / W) % H);
+        const float* img = x + (p / ((long long)W * H)) * (long long)H * W;
+        float v[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+          const int yy = py + k / 3 - 1, xx = px + k % 3 - 1;
+          v[k] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(img + (long long)yy * W + xx) : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
+          pk[k] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+        const __nv_bfloat162 h = __floats2bfloat162_rn(v[8], 0.f);
+        pk[4] = *reinterpret_cast<const uint32_t*>(&h);
+      }
+      uint8_t* row = sm.a[buf] + (r >> 3) * 256 + (r & 7) * 16;
+      *reinterpret_cast<uint4*>(row) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      *reinterpret_cast<uint4*>(row + 128) = make_uint4(pk[4], 0, 0, 0);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive(a_full(buf));
+    };
+    int it = 0;
+    if (blockIdx.x < ntiles) build(blockIdx.x, 0);
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+      const int buf = it & 1, ph = (it >> 1) & 1;
+      if (t + (int)gridDim.x < ntiles) build(t + gridDim.x, buf ^ 1);
+      // the TMA store that last read stage[buf] (two tiles ago) must have drained before we overwrite it
+      if (threadIdx.x == 0) tma_store_wait_read<1>();
+      named_bar_sync(1, 128);
+      mbar_wait(acc_full(buf), ph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + buf * 64 + ((uint32_t)(warp * 32) << 16);
+      uint8_t* srow = sm.stage[buf] + r * 128;
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        uint32_t v[32];
+        tc_ld_nowait<32>(taddr + b * 32, v);
+        tc_wait_ld();
+        if (b == 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(acc_empty(buf));
+        }
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          const float4 b0 = *reinterpret_cast<const float4*>(sm.bias + b * 32 + j);
+          const float4 b1 = *reinterpret_cast<const float4*>(sm.bias + b * 32 + j + 4);
+          const __nv_bfloat162 h0 = __floats2bfloat162_rn(fmaxf(__uint_as_float(v[j]) + b0.x, 0.f),
+                                                          fmaxf(__uint_as_float(v[j + 1]) + b0.y, 0.f));
+          const __nv_bfloat162 h1 = __floats2bfloat162_rn(fmaxf(__uint_as_float(v[j + 2]) + b0.z, 0.f),
+                                                          fmaxf(__uint_as_float(v[j + 3]) + b0.w, 0.f));
+          const __nv_bfloat162 h2 = __floats2bfloat162_rn(fmaxf(__uint_as_float(v[j + 4]) + b1.x, 0.f),
+                                                          fmaxf(__uint_as_float(v[j + 5]) + b1.y, 0.f));
+          const __nv_bfloat162 h3 = __floats2bfloat162_rn(fmaxf(__uint_as_float(v[j + 6]) + b1.z, 0.f),
+                                                          fmaxf(__uint_as_float(v[j + 7]) + b1.w, 0.f));
+          const int chunk = (b * 4 + j / 8) ^ (r & 7);  // SWIZZLE_128B: 16-byte chunk XOR (row mod 8)
+          *reinterpret_cast<uint4*>(srow + chunk * 16) =
+              make_uint4(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1),
+                         *reinterpret_cast<const uint32_t*>(&h2), *reinterpret_cast<const uint32_t*>(&h3));
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      named_bar_sync(1, 128);
+      if (threadIdx.x == 0) {
+        tma_store_2d(&tm_out, smem_u32(sm.stage[buf]), 0, t * 128);  // rows beyond npix are clipped by TMA
+        tma_store_commit();
+      }
+    }
+    if (threadIdx.x == 0) tma_store_wait_read<0>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -530,6 +705,35 @@ static int encode_act_map(CUtensorMap* tm, const void* in, int B, int H, int W, 
               boxw, boxh, (int)r);
     return SPB_ECUDA;
   }
+  return SPB_OK;
+}
+
+int conv1a_tc(const LayerDev& L, const float* x, __nv_bfloat16* out, int B, int H, int W, cudaStream_t st) {
+  const long long npix = (long long)B * H * W;
+  const int ntiles = ceil_div(npix, 128);
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_error("conv1a_tc: cuTensorMapEncodeTiled not available from the driver");
+    return SPB_ECUDA;
+  }
+  CUtensorMap tm;
+  cuuint64_t dims[2] = {64, (cuuint64_t)npix};
+  cuuint64_t strides[1] = {128};
+  cuuint32_t box[2] = {64, 128};
+  cuuint32_t es[2] = {1, 1};
+  const CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, out, dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("conv1a_tc: cuTensorMapEncodeTiled(output) failed with CUresult %d", (int)r);
+    return SPB_ECUDA;
+  }
+  const int smem = (int)sizeof(Conv1aSmem) + 1024;
+  SPB_CHECK_CUDA(cudaFuncSetAttribute(conv1a_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  int grid = kNumSMs * 4;
+  if (grid > ntiles) grid = ntiles;
+  conv1a_tc_kernel<<<grid, 160, smem, st>>>(tm, x, L.w_tc, L.bias, npix, H, W, ntiles);
+  SPB_CHECK_LAUNCH();
   return SPB_OK;
 }
 

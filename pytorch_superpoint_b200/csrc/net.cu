@@ -83,7 +83,10 @@ static int run_layer(const Net* net, int li, const void* in, void* out, int B, i
                      cudaStream_t st) {
   const LayerDev& L = net->layer[li];
   StageTimer tm(net, li, st);
-  if (li == 0) return conv1a_simt(L, static_cast<const float*>(in), static_cast<__nv_bfloat16*>(out), B, H, W, st);
+  if (li == 0)
+    return net->impl == SPB_IMPL_TCGEN05
+               ? conv1a_tc(L, static_cast<const float*>(in), static_cast<__nv_bfloat16*>(out), B, H, W, st)
+               : conv1a_simt(L, static_cast<const float*>(in), static_cast<__nv_bfloat16*>(out), B, H, W, st);
   if (net->impl == SPB_IMPL_TCGEN05)
     return conv_tc(L, static_cast<const __nv_bfloat16*>(in), out, B, H, W, out_mode, st);
   if (out_mode == 3) {
@@ -165,7 +168,8 @@ int spb_net_create(spb_net** out, const float* const* weights, const float* cons
     L.cout_pad = (S.cout + 15) / 16 * 16;
     const int taps = S.ks * S.ks, K = taps * S.cin;
     std::vector<__nv_bfloat16> ws((size_t)taps * S.cin * L.cout_pad, __float2bfloat16(0.f));
-    std::vector<__nv_bfloat16> wt((size_t)L.cout_pad * K, __float2bfloat16(0.f));
+    const int Kpad = (li == 0) ? 16 : K;  // conv1a: 9 taps padded to one UMMA K step
+    std::vector<__nv_bfloat16> wt((size_t)L.cout_pad * Kpad, __float2bfloat16(0.f));
     std::vector<float> b(L.cout_pad, 0.f);
     const float* w = weights[li];  // OIHW
     for (int co = 0; co < S.cout; ++co) {
@@ -174,7 +178,7 @@ int spb_net_create(spb_net** out, const float* const* weights, const float* cons
         for (int t = 0; t < taps; ++t) {
           const __nv_bfloat16 v = __float2bfloat16_rn(w[((size_t)co * S.cin + ci) * taps + t]);
           ws[((size_t)t * S.cin + ci) * L.cout_pad + co] = v;
-          wt[(size_t)co * K + (size_t)t * S.cin + ci] = v;
+          wt[(size_t)co * Kpad + (size_t)t * S.cin + ci] = v;
         }
     }
     SPB_CHECK_CUDA(cudaMalloc(&L.bias, b.size() * sizeof(float)));

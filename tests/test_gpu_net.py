@@ -79,6 +79,21 @@ def test_tcgen05_layer_vs_reference(net, li, B, H, W, halo):
     assert (tc - simt).abs().max().item() <= (3.2e-2 if li not in (9, 11) else 1e-4)
 
 
+@pytest.mark.parametrize("B,H,W", [(1, 16, 8), (3, 24, 40), (2, 240, 320), (5, 30, 52)])
+def test_conv1a_tensor_core_vs_simt(net, B, H, W):
+    """conv1a as a K=16 im2col MMA: same bf16 numerics as the CUDA-core kernel, incl. ragged last tile."""
+    x = torch.rand(B, H, W, device="cuda", generator=torch.Generator("cuda").manual_seed(H))
+    simt = _layer(net, 0, x, B, H, W, "simt").float()
+    tc = _layer(net, 0, x, B, H, W, "tcgen05").float()
+    p = O.fold_bn(O.canonical_params(O.synthetic_state_dict("gauss2", seed=1)))["conv1a"]
+    ref = torch.relu(torch.nn.functional.conv2d(x[:, None].to(torch.bfloat16).float(),
+                                                p["w"].to(torch.bfloat16).float().cuda(), p["b"].cuda(), padding=1))
+    ref = ref.permute(0, 2, 3, 1)
+    assert torch.isfinite(tc).all()
+    assert (tc - ref).abs().max().item() < 2e-2 and (simt - ref).abs().max().item() < 2e-2
+    assert (tc - simt).abs().max().item() <= 1.6e-2
+
+
 @pytest.mark.parametrize("impl", ["simt", "tcgen05"])
 @pytest.mark.parametrize("layout", ["gauss2", "bnflat", "v1"])
 def test_forward_vs_reference_golden(impl, layout, golden):
