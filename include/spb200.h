@@ -78,6 +78,7 @@ int spb_ha_aggregate(const float* semi_nhwc, int cstride, const float* mats_unwa
                      int N, int H, int W, float* sums, int accumulate, void* ws, size_t ws_bytes, void* stream);
 /* export.py:63 the final division (after the NCCL all-reduce of `sums` when N is sharded). */
 int spb_ha_finalize(const float* sums, float* heat, int H, int W, void* stream);
+int spb_ha_finalize_batch(const float* sums /*[B,2,H,W]*/, float* heat /*[B,H,W]*/, int B, int H, int W, void* stream);
 
 /* ---- (4) threshold + greedy grid NMS + border removal + top-k -----------------------------------
  * models/model_wrap.py:252-279 `getPtsFromHeatmap` incl. `nms_fast` (117-180) and export.py:322-328
@@ -141,6 +142,14 @@ int spb_net_layer(spb_net* net, int layer, const void* in, void* out, int B, int
 size_t spb_ha_workspace_bytes(int N, int H, int W);
 int spb_ha_heatmap_sums(spb_net* net, const float* img, const float* mats_unwarp, const float* mats_fwd,
                         int N, int H, int W, float* sums, int accumulate, void* ws, size_t ws_bytes, void* stream);
+/* Same for a batch of B images in one set of launches (export.py's per-image loop, batched so that a shard of
+ * 12-13 views per image still fills the GPU): imgs [B,H,W]; matrices [N,3,3] shared by all images
+ * (shared_mats != 0) or [B,N,3,3]; sums [B,2,H,W].  Views are processed in passes of at most
+ * spb_net_set_ha_chunk views (default 800). */
+size_t spb_ha_workspace_bytes_batch(spb_net* net, int B, int N, int H, int W);
+int spb_ha_heatmap_sums_batch(spb_net* net, const float* imgs, const float* mats_unwarp, const float* mats_fwd,
+                              int shared_mats, int B, int N, int H, int W, float* sums, int accumulate, void* ws,
+                              size_t ws_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -30,6 +30,7 @@ PROTOTYPES = {
     "spb_ha_aggregate_workspace_bytes": (_z, [_i, _i, _i]),
     "spb_ha_aggregate": (_i, [_p, _i, _p, _p, _i, _i, _i, _p, _i, _p, _z, _p]),
     "spb_ha_finalize": (_i, [_p, _p, _i, _i, _p]),
+    "spb_ha_finalize_batch": (_i, [_p, _p, _i, _i, _i, _p]),
     "spb_nms_workspace_bytes": (_z, [_i, _i, _i, _i]),
     "spb_get_pts_from_heatmap": (_i, [_p, _i, _i, _i, _f, _i, _i, _i, _i, _p, _p, _p, _p, _z, _p]),
     "spb_sample_desc_from_points": (_i, [_p, _i, _p, _p, _i, _i, _i, _i, _i, _p, _p]),
@@ -45,6 +46,8 @@ PROTOTYPES = {
     "spb_net_layer": (_i, [_p, _i, _p, _p, _i, _i, _i, _p]),
     "spb_ha_workspace_bytes": (_z, [_i, _i, _i]),
     "spb_ha_heatmap_sums": (_i, [_p, _p, _p, _p, _i, _i, _i, _p, _i, _p, _z, _p]),
+    "spb_ha_workspace_bytes_batch": (_z, [_p, _i, _i, _i, _i]),
+    "spb_ha_heatmap_sums_batch": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _i, _p, _z, _p]),
 }
 # debug knobs exported by the library but not part of the public header
 _EXTRA = {"spb_conv_tc_set_halo": (_i, [_i])}

@@ -225,16 +225,21 @@ __global__ void __launch_bounds__(256) ha_aggregate_kernel(AggParams p) {
 // HA product path: the detector head's epilogue already wrote softmax probabilities (dustbin dropped) as
 // probs[N,Hc,Wc,64] and the warp kernel wrote the valid-mask bits, so aggregation is a pure gather:
 // one thread per output pixel, views n = g, g+G, ... accumulated in registers in a fixed order.
+// blockIdx.z = image * G + group; image b owns views [b*N, (b+1)*N) of probs / bits.
 __global__ void __launch_bounds__(256) agg_probs_kernel(const float* __restrict__ probs,
                                                         const uint8_t* __restrict__ bits,
-                                                        const float* __restrict__ mu, int N, int H, int W, int G,
-                                                        float* __restrict__ part, Lin lx, Lin ly) {
+                                                        const float* __restrict__ mu, int shared_mats, int N, int H,
+                                                        int W, int G, float* __restrict__ part, Lin lx, Lin ly) {
   const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
   if (x >= W || y >= H) return;
   const int Wc = W >> 3, Hc = H >> 3;
+  const int b = blockIdx.z / G, g = blockIdx.z % G;
+  probs += (long long)b * N * Hc * Wc * 64;
+  bits += (long long)b * N * H * Wc;
+  if (!shared_mats) mu += (long long)b * N * 9;
   const float u = lx.at(x), v = ly.at(y);
   float num = 0.f, den = 0.f;
-  for (int n = blockIdx.z; n < N; n += G) {
+  for (int n = g; n < N; n += G) {
     const Mat3 M = load_mat(mu + 9 * n);
     float ix, iy;
     warp_coord(M, u, v, W, H, ix, iy);
@@ -262,11 +267,14 @@ __global__ void __launch_bounds__(256) agg_probs_kernel(const float* __restrict_
   o[(long long)H * W] = den;
 }
 
+// sums[b][i] (+)= sum_g part[b][g][i], fixed order; n = elements per image (2*H*W), total = B*n
 __global__ void __launch_bounds__(256) agg_reduce_kernel(const float* __restrict__ part, int G, long long n,
-                                                         float* __restrict__ sums, int accumulate) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+                                                         long long total, float* __restrict__ sums, int accumulate) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / n, r = i % n;
     float s = accumulate ? sums[i] : 0.f;
-    for (int g = 0; g < G; ++g) s = __fadd_rn(s, part[(long long)g * n + i]);
+    for (int g = 0; g < G; ++g) s = __fadd_rn(s, part[(b * G + g) * n + r]);
     sums[i] = s;
   }
 }
@@ -277,6 +285,15 @@ __global__ void __launch_bounds__(256) finalize_kernel(const float* __restrict__
     heat[i] = __fdiv_rn(sums[i], sums[n + i]);
 }
 
+__global__ void __launch_bounds__(256) finalize_batch_kernel(const float* __restrict__ sums, float* __restrict__ heat,
+                                                             long long n, long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / n, r = i % n;
+    heat[i] = __fdiv_rn(sums[b * 2 * n + r], sums[b * 2 * n + n + r]);
+  }
+}
+
 static int agg_groups(int N, int H, int W) {
   const int tiles = ceil_div(W, kAggTile) * ceil_div(H, kAggTile);
   int G = ceil_div(3LL * kNumSMs * 6, tiles);  // ~3 waves of 6 resident CTAs per SM
@@ -285,19 +302,27 @@ static int agg_groups(int N, int H, int W) {
   return G;
 }
 
-int aggregate_probs(const float* probs, const uint8_t* bits, const float* mats_unwarp, int N, int H, int W,
-                    float* sums, int accumulate, void* ws, cudaStream_t st) {
+int aggregate_probs_groups(int B, int N, int H, int W) {
   const int tiles = ceil_div(W, 32) * ceil_div(H, 8);
-  int G = ceil_div(4LL * kNumSMs * 8, tiles);
+  int G = ceil_div(4LL * kNumSMs * 8, (long long)tiles * B);
   if (G > N) G = N;
-  if (G > agg_groups(N, H, W)) G = agg_groups(N, H, W);  // never exceed the workspace sized by the public call
   if (G < 1) G = 1;
+  return G;
+}
+size_t aggregate_probs_workspace(int B, int N, int H, int W) {
+  return (size_t)B * aggregate_probs_groups(B, N, H, W) * 2 * H * W * sizeof(float);
+}
+
+// B images x N views each (probs / bits contiguous over b*N + n); sums [B,2,H,W]
+int aggregate_probs(const float* probs, const uint8_t* bits, const float* mats_unwarp, int shared_mats, int B, int N,
+                    int H, int W, float* sums, int accumulate, void* ws, cudaStream_t st) {
+  const int G = aggregate_probs_groups(B, N, H, W);
   float* part = static_cast<float*>(ws);
-  dim3 grid(ceil_div(W, 32), ceil_div(H, 8), G);
-  agg_probs_kernel<<<grid, 256, 0, st>>>(probs, bits, mats_unwarp, N, H, W, G, part, Lin(W), Lin(H));
+  dim3 grid(ceil_div(W, 32), ceil_div(H, 8), G * B);
+  agg_probs_kernel<<<grid, 256, 0, st>>>(probs, bits, mats_unwarp, shared_mats, N, H, W, G, part, Lin(W), Lin(H));
   SPB_CHECK_LAUNCH();
-  const long long n = 2LL * H * W;
-  agg_reduce_kernel<<<min(ceil_div(n, 256), kNumSMs * 8), 256, 0, st>>>(part, G, n, sums, accumulate);
+  const long long n = 2LL * H * W, total = n * B;
+  agg_reduce_kernel<<<min(ceil_div(total, 256), kNumSMs * 8), 256, 0, st>>>(part, G, n, total, sums, accumulate);
   SPB_CHECK_LAUNCH();
   return SPB_OK;
 }
@@ -364,7 +389,15 @@ int spb_ha_aggregate(const float* semi_nhwc, int cstride, const float* mats_unwa
   ha_aggregate_kernel<<<grid, 256, 0, as_stream(stream)>>>(p);
   SPB_CHECK_LAUNCH();
   const long long n = 2LL * H * W;
-  agg_reduce_kernel<<<min(ceil_div(n, 256), kNumSMs * 8), 256, 0, as_stream(stream)>>>(p.part, p.G, n, sums, accumulate);
+  agg_reduce_kernel<<<min(ceil_div(n, 256), kNumSMs * 8), 256, 0, as_stream(stream)>>>(p.part, p.G, n, n, sums, accumulate);
+  SPB_CHECK_LAUNCH();
+  return SPB_OK;
+}
+
+int spb_ha_finalize_batch(const float* sums, float* heat, int B, int H, int W, void* stream) {
+  SPB_CHECK_ARG(sums && heat && B > 0 && H > 0 && W > 0);
+  const long long n = (long long)H * W, total = n * B;
+  finalize_batch_kernel<<<min(ceil_div(total, 256), kNumSMs * 8), 256, 0, as_stream(stream)>>>(sums, heat, n, total);
   SPB_CHECK_LAUNCH();
   return SPB_OK;
 }

@@ -253,67 +253,105 @@ int spb_net_layer(spb_net* h, int layer, const void* in, void* out, int B, int H
 }
 
 // ---- whole HA step ----------------------------------------------------------------------------------
-static void ha_layout(int n, int H, int W, size_t& off_warp, size_t& off_semi, size_t& off_agg, size_t& off_net,
-                      size_t& total) {
+// One pass = Bg images x n views each through warp -> detector net -> gather-aggregate.
+struct HaLayout {
+  size_t warp, bits, semi, probs, agg, net, total;
+};
+static HaLayout ha_layout(int Bg, int n, int H, int W) {
+  const size_t V = (size_t)Bg * n, cells = (size_t)(H / 8) * (W / 8);
+  HaLayout L;
   size_t o = 0;
-  off_warp = o;
-  o += align_up((size_t)n * H * W * 4, 1024);
-  o += align_up((size_t)n * H * (W / 8), 1024);  // valid-mask bits follow the warped views
-  off_semi = o;
-  o += align_up((size_t)n * (H / 8) * (W / 8) * 65 * 4, 1024);  // probabilities [.,64] (or logits [.,65] in SIMT mode)
-  o += align_up((size_t)n * (H / 8) * (W / 8) * 64 * 4, 1024);
-  off_agg = o;
-  o += align_up(spb_ha_aggregate_workspace_bytes(n, H, W), 1024);
-  off_net = o;
-  o += spb_net_workspace_bytes(n, H, W, 0);
-  total = o;
+  L.warp = o;
+  o += align_up(V * H * W * 4, 1024);
+  L.bits = o;
+  o += align_up(V * H * (W / 8), 1024);
+  L.semi = o;  // logits: SIMT validation path only
+  o += align_up(V * cells * 65 * 4, 1024);
+  L.probs = o;
+  o += align_up(V * cells * 64 * 4, 1024);
+  L.agg = o;
+  o += align_up(aggregate_probs_workspace(Bg, n, H, W), 1024);
+  L.net = o;
+  o += spb_net_workspace_bytes((int)V, H, W, 0);
+  L.total = o + 1024;
+  return L;
+}
+
+static void ha_plan(const Net* net, int B, int N, int& Bg, int& n) {
+  const int cap = net->ha_chunk > 0 ? net->ha_chunk : 800;  // views per pass
+  if (cap >= N) {
+    n = N;
+    Bg = cap / N;
+    if (Bg > B) Bg = B;
+  } else {
+    n = cap;
+    Bg = 1;
+  }
+}
+
+size_t spb_ha_workspace_bytes_batch(spb_net* h, int B, int N, int H, int W) {
+  if (!h || B < 1 || N < 1 || H < 8 || W < 8) return 0;
+  int Bg, n;
+  ha_plan(reinterpret_cast<Net*>(h), B, N, Bg, n);
+  return ha_layout(Bg, n, H, W).total;
 }
 
 size_t spb_ha_workspace_bytes(int N, int H, int W) {
   if (N < 1 || H < 8 || W < 8) return 0;
-  size_t a, b, c, d, t;
-  ha_layout(N, H, W, a, b, c, d, t);
-  return t + 1024;
+  return ha_layout(1, N, H, W).total;  // an upper bound for every chunk setting of a single image
+}
+
+int spb_ha_heatmap_sums_batch(spb_net* h, const float* imgs, const float* mats_unwarp, const float* mats_fwd,
+                              int shared_mats, int B, int N, int H, int W, float* sums, int accumulate, void* ws,
+                              size_t ws_bytes, void* stream) {
+  SPB_CHECK_ARG(h && imgs && mats_unwarp && mats_fwd && sums && ws);
+  SPB_CHECK_ARG(B >= 1 && N >= 1 && H >= 8 && W >= 8 && H % 8 == 0 && W % 8 == 0);
+  Net* net = reinterpret_cast<Net*>(h);
+  int Bg, n;
+  ha_plan(net, B, N, Bg, n);
+  const HaLayout L = ha_layout(Bg, n, H, W);
+  if (ws_bytes < L.total) {
+    set_error("spb_ha_heatmap_sums: workspace %zu < %zu bytes", ws_bytes, L.total);
+    return SPB_ENOMEM;
+  }
+  char* base = static_cast<char*>(align_ptr(ws));
+  float* warped = reinterpret_cast<float*>(base + L.warp);
+  uint8_t* bits = reinterpret_cast<uint8_t*>(base + L.bits);
+  float* semi = reinterpret_cast<float*>(base + L.semi);
+  float* probs = reinterpret_cast<float*>(base + L.probs);
+  const bool tc = net->impl == SPB_IMPL_TCGEN05;
+  cudaStream_t st = as_stream(stream);
+  for (int b0 = 0; b0 < B; b0 += Bg) {
+    const int bg = (B - b0 < Bg) ? B - b0 : Bg;
+    for (int n0 = 0; n0 < N; n0 += n) {  // more than one trip only when a single image is split into view chunks
+      const int nn = (N - n0 < n) ? N - n0 : n;
+      const long long moff = shared_mats ? 9LL * n0 : 9LL * ((long long)b0 * N + n0);
+      // per-image matrix sets are only contiguous over a whole image: view chunks imply bg == 1
+      int rc;
+      {
+        StageTimer tm(net, 12, st);
+        rc = warp_with_mask_bits(imgs + (long long)b0 * H * W, mats_fwd + moff, warped, bits, bg * nn, nn, shared_mats,
+                                 H, W, st);
+      }
+      if (rc != SPB_OK) return rc;
+      // the detector head writes softmax probabilities directly (tcgen05 epilogue); the validation path goes
+      // through logits + a softmax kernel
+      rc = forward(net, warped, bg * nn, H, W, tc ? nullptr : semi, probs, nullptr, base + L.net, st);
+      if (rc != SPB_OK) return rc;
+      {
+        StageTimer tm(net, 13, st);
+        rc = aggregate_probs(probs, bits, mats_unwarp + moff, shared_mats, bg, nn, H, W,
+                             sums + (long long)b0 * 2 * H * W, accumulate || n0 > 0, base + L.agg, st);
+      }
+      if (rc != SPB_OK) return rc;
+    }
+  }
+  return SPB_OK;
 }
 
 int spb_ha_heatmap_sums(spb_net* h, const float* img, const float* mats_unwarp, const float* mats_fwd, int N, int H,
                         int W, float* sums, int accumulate, void* ws, size_t ws_bytes, void* stream) {
-  SPB_CHECK_ARG(h && img && mats_unwarp && mats_fwd && sums && ws);
-  SPB_CHECK_ARG(N >= 1 && H >= 8 && W >= 8 && H % 8 == 0 && W % 8 == 0);
-  Net* net = reinterpret_cast<Net*>(h);
-  const int chunk = (net->ha_chunk > 0 && net->ha_chunk < N) ? net->ha_chunk : N;
-  size_t o_warp, o_semi, o_agg, o_net, total;
-  ha_layout(chunk, H, W, o_warp, o_semi, o_agg, o_net, total);
-  if (ws_bytes < total + 1024) {
-    set_error("spb_ha_heatmap_sums: workspace %zu < %zu bytes", ws_bytes, total + 1024);
-    return SPB_ENOMEM;
-  }
-  char* base = static_cast<char*>(align_ptr(ws));
-  float* warped = reinterpret_cast<float*>(base + o_warp);
-  uint8_t* bits = reinterpret_cast<uint8_t*>(base + o_warp + align_up((size_t)chunk * H * W * 4, 1024));
-  float* semi = reinterpret_cast<float*>(base + o_semi);
-  float* probs = reinterpret_cast<float*>(base + o_semi + align_up((size_t)chunk * (H / 8) * (W / 8) * 65 * 4, 1024));
-  const bool tc = net->impl == SPB_IMPL_TCGEN05;
-  for (int n0 = 0; n0 < N; n0 += chunk) {
-    const int n = (N - n0 < chunk) ? N - n0 : chunk;
-    int rc;
-    {
-      StageTimer tm(net, 12, as_stream(stream));
-      rc = warp_with_mask_bits(img, mats_fwd + 9 * n0, warped, bits, n, H, W, as_stream(stream));
-    }
-    if (rc != SPB_OK) return rc;
-    // the detector head writes softmax probabilities directly (tcgen05 epilogue); the validation path goes
-    // through logits + a softmax kernel
-    rc = forward(net, warped, n, H, W, tc ? nullptr : semi, probs, nullptr, base + o_net, as_stream(stream));
-    if (rc != SPB_OK) return rc;
-    {
-      StageTimer tm(net, 13, as_stream(stream));
-      rc = aggregate_probs(probs, bits, mats_unwarp + 9 * n0, n, H, W, sums, accumulate || n0 > 0, base + o_agg,
-                           as_stream(stream));
-    }
-    if (rc != SPB_OK) return rc;
-  }
-  return SPB_OK;
+  return spb_ha_heatmap_sums_batch(h, img, mats_unwarp, mats_fwd, 1, 1, N, H, W, sums, accumulate, ws, ws_bytes, stream);
 }
 
 int spb_net_profile(spb_net* h, int on) {

@@ -63,9 +63,10 @@ __global__ void __launch_bounds__(256) warp_kernel(const float* __restrict__ img
 // HA variant: bilinear warp of ONE image into N views + the nearest-mode valid mask of the same coordinates
 // (utils/utils.py:696 uses the same grid and matrices as the image warp, datasets/Coco.py:279-282), packed one
 // bit per pixel: bits[(n*H + y)*(W/8) + x/8] bit (x%8).  Needs W % 8 == 0.
+// View n belongs to image n / vpi; its matrix is mats[n] (per-image sets, contiguous) or mats[n % vpi] (shared).
 __global__ void __launch_bounds__(256) warp_bits_kernel(const float* __restrict__ img, const float* __restrict__ mats,
                                                         float* __restrict__ out, uint8_t* __restrict__ bits, int N,
-                                                        int H, int W, Lin lx, Lin ly) {
+                                                        int vpi, int shared_mats, int H, int W, Lin lx, Lin ly) {
   const int Wq = W >> 2;
   const long long total = (long long)N * H * Wq;
   const int lane = threadIdx.x & 31;
@@ -76,7 +77,8 @@ __global__ void __launch_bounds__(256) warp_bits_kernel(const float* __restrict_
     const int xq = (int)(tt % Wq);
     const int y = (int)((tt / Wq) % H);
     const int n = (int)(tt / ((long long)Wq * H));
-    const Mat3 M = load_mat(mats + 9 * n);
+    const Mat3 M = load_mat(mats + 9 * (shared_mats ? n % vpi : n));
+    const float* src = img + (long long)(n / vpi) * H * W;
     const float v = ly.at(y);
     float r[4];
     unsigned nib = 0;
@@ -85,7 +87,7 @@ __global__ void __launch_bounds__(256) warp_bits_kernel(const float* __restrict_
       float ix, iy;
       warp_coord(M, lx.at(xq * 4 + j), v, W, H, ix, iy);
       const Taps tp = make_taps(ix, iy);
-      r[j] = bilinear(tp, W, H, [&](int xx, int yy) { return __ldg(img + (long long)yy * W + xx); });
+      r[j] = bilinear(tp, W, H, [&](int xx, int yy) { return __ldg(src + (long long)yy * W + xx); });
       nib |= (in_bounds(rintf(ix), rintf(iy), W, H) ? 1u : 0u) << j;
     }
     const unsigned hi = __shfl_down_sync(0xffffffffu, nib, 1);
@@ -96,12 +98,12 @@ __global__ void __launch_bounds__(256) warp_bits_kernel(const float* __restrict_
   }
 }
 
-int warp_with_mask_bits(const float* img, const float* mats, float* out, uint8_t* bits, int N, int H, int W,
-                        cudaStream_t st) {
+int warp_with_mask_bits(const float* img, const float* mats, float* out, uint8_t* bits, int N, int vpi,
+                        int shared_mats, int H, int W, cudaStream_t st) {
   const long long total = (long long)N * H * (W / 4);
   int blocks = ceil_div(total, 256);
   if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
-  warp_bits_kernel<<<blocks, 256, 0, st>>>(img, mats, out, bits, N, H, W, Lin(W), Lin(H));
+  warp_bits_kernel<<<blocks, 256, 0, st>>>(img, mats, out, bits, N, vpi, shared_mats, H, W, Lin(W), Lin(H));
   SPB_CHECK_LAUNCH();
   return SPB_OK;
 }

@@ -44,15 +44,18 @@ class HAExporter:
             d1 = self.nms_dist + 1
             cap = self.top_k if self.top_k else -(-H // d1) * -(-W // d1)
             dev = self.device
-            self._bufs = {key: dict(
-                img=torch.empty((B, H, W), device=dev, dtype=torch.float32),
-                sums=torch.empty((B, 2, H, W), device=dev, dtype=torch.float32),
-                heat=torch.empty((B, H, W), device=dev, dtype=torch.float32),
-                pts_host=torch.empty((B, cap, 3), dtype=torch.float32).pin_memory(),
-                cnt_host=torch.empty((B,), dtype=torch.int32).pin_memory(), cap=cap)}
+            slots = [dict(heat=torch.empty((B, H, W), device=dev, dtype=torch.float32),
+                          pts_host=torch.empty((B, cap, 3), dtype=torch.float32).pin_memory(),
+                          cnt_host=torch.empty((B,), dtype=torch.int32).pin_memory(),
+                          done=None, mine=[]) for _ in range(2)]
+            self._bufs = {key: dict(img=torch.empty((B, H, W), device=dev, dtype=torch.float32),
+                                    sums=torch.empty((B, 2, H, W), device=dev, dtype=torch.float32),
+                                    slots=slots, cap=cap, k=0)}
+            self._side = torch.cuda.Stream(device=dev)
         return self._bufs[key]
 
-    def heatmaps(self, imgs_dev: torch.Tensor, mats_unwarp: torch.Tensor, mats_fwd: torch.Tensor) -> torch.Tensor:
+    def heatmaps(self, imgs_dev: torch.Tensor, mats_unwarp: torch.Tensor, mats_fwd: torch.Tensor,
+                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """imgs_dev [B,H,W] cuda; mats [N,3,3] (shared by the batch) or [B,N,3,3] -> aggregated heat [B,H,W]."""
         B, H, W = imgs_dev.shape
         buf = self._buffers(B, H, W)
@@ -61,61 +64,82 @@ class HAExporter:
         N = mats_unwarp.shape[-3]
         lo, hi = shard_bounds(N, rank, world)
         sums = buf["sums"]
-        for b in range(B):
-            mu = mats_unwarp[b] if per_image else mats_unwarp
-            mf = mats_fwd[b] if per_image else mats_fwd
-            if hi > lo:
-                self.net.ha_heatmap_sums(imgs_dev[b], mu[lo:hi], mf[lo:hi], sums=sums[b], chunk=self.chunk)
-            else:
-                sums[b].zero_()
+        if hi > lo:
+            mu = mats_unwarp[:, lo:hi] if per_image else mats_unwarp[lo:hi]
+            mf = mats_fwd[:, lo:hi] if per_image else mats_fwd[lo:hi]
+            self.net.ha_heatmap_sums_batch(imgs_dev, mu, mf, sums=sums, chunk=self.chunk)
+        else:
+            sums.zero_()
         if world > 1:
             dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=self.group)
+        # export.py:63 -- [B,2,H,W] sums -> [B,H,W] heat: one launch over the batch (sums[b,0]/sums[b,1])
+        heat = out if out is not None else buf["slots"][0]["heat"]
         from . import _lib
-        L = _lib.lib()
-        st = torch.cuda.current_stream().cuda_stream
-        for b in range(B):
-            _lib.check(L.spb_ha_finalize(sums[b].data_ptr(), buf["heat"][b].data_ptr(), H, W, st), "ha_finalize")
-        return buf["heat"]
+        _lib.check(_lib.lib().spb_ha_finalize_batch(sums.data_ptr(), heat.data_ptr(), B, H, W,
+                                                    torch.cuda.current_stream().cuda_stream), "ha_finalize")
+        return heat
 
-    def export_batch(self, imgs_host: Sequence[torch.Tensor], mats_unwarp: torch.Tensor, mats_fwd: torch.Tensor,
-                     sync: bool = True):
-        """imgs_host: B pinned (or pageable) CPU tensors [H,W] fp32.  Returns a list of float64 [K,3] arrays for
-        the images this rank owns (``b % world == rank``; None for the others).  H2D, compute and D2H are all
-        enqueued on the current stream; one synchronisation at the end."""
+    def submit_resident(self, imgs_dev: torch.Tensor, mats_unwarp: torch.Tensor, mats_fwd: torch.Tensor):
+        """Device-resident inputs -> enqueue heat-maps on the current stream and NMS/top-k + the D2H of the
+        key-points on a side stream, so they overlap the next batch's convolutions.  Returns a ticket for collect()."""
+        B, H, W = imgs_dev.shape
+        buf = self._buffers(B, H, W)
+        rank, world = world_info(self.group)
+        slot = buf["slots"][buf["k"] & 1]
+        buf["k"] += 1
+        main = torch.cuda.current_stream()
+        if slot["done"] is not None:
+            main.wait_event(slot["done"])  # the side stream still reads this slot's heat-map from two batches ago
+        heat = self.heatmaps(imgs_dev, mats_unwarp, mats_fwd, out=slot["heat"])
+        ready = torch.cuda.Event()
+        ready.record(main)
+        mine = [b for b in range(B) if owner_of_image(b, world) == rank]
+        slot["mine"] = mine
+        self._side.wait_event(ready)
+        with torch.cuda.stream(self._side):
+            if mine:
+                sel = heat[mine].contiguous() if len(mine) < B else heat
+                pts, counts, _ = ops.get_pts_from_heatmap_device(sel, self.conf_thresh, self.nms_dist,
+                                                                 self.border_remove, self.top_k, buf["cap"])
+                slot["pts_host"][:len(mine)].copy_(pts, non_blocking=True)
+                slot["cnt_host"][:len(mine)].copy_(counts, non_blocking=True)
+            slot["done"] = torch.cuda.Event()
+            slot["done"].record(self._side)
+        return slot
+
+    def submit(self, imgs_host: Sequence[torch.Tensor], mats_unwarp: torch.Tensor, mats_fwd: torch.Tensor):
+        """Host images in (pinned for true async copies): H2D + submit_resident.  Returns a ticket for collect()."""
         B = len(imgs_host)
         H, W = imgs_host[0].shape[-2:]
         buf = self._buffers(B, H, W)
-        rank, world = world_info(self.group)
         with torch.cuda.device(self.device):
             for b in range(B):
                 buf["img"][b].copy_(imgs_host[b].reshape(H, W), non_blocking=True)
             mu = mats_unwarp.to(self.device, torch.float32, non_blocking=True)
             mf = mats_fwd.to(self.device, torch.float32, non_blocking=True)
-            heat = self.heatmaps(buf["img"], mu, mf)
-            mine = [b for b in range(B) if owner_of_image(b, world) == rank]
-            if mine:
-                sel = heat[mine] if len(mine) < B else heat
-                pts, counts, _ = ops.get_pts_from_heatmap_device(sel.contiguous(), self.conf_thresh, self.nms_dist,
-                                                                 self.border_remove, self.top_k, buf["cap"])
-                buf["pts_host"][:len(mine)].copy_(pts, non_blocking=True)
-                buf["cnt_host"][:len(mine)].copy_(counts, non_blocking=True)
-            if sync:
-                torch.cuda.current_stream().synchronize()
-        self._last = (mine, buf)
-        return self.collect() if sync else None
+            return self.submit_resident(buf["img"], mu, mf)
 
-    def collect(self) -> List[Optional[np.ndarray]]:
-        mine, buf = self._last
-        B = buf["img"].shape[0]
+    def collect(self, ticket) -> List[Optional[np.ndarray]]:
+        """Wait for a ticket; float64 [K,3] (x, y, conf) per image this rank owns (b % world == rank), else None."""
+        ticket["done"].synchronize()
+        B = ticket["heat"].shape[0]
         out: List[Optional[np.ndarray]] = [None] * B
-        for j, b in enumerate(mine):
-            k = int(buf["cnt_host"][j])
-            out[b] = buf["pts_host"][j, :k].numpy().astype(np.float64)
+        for j, b in enumerate(ticket["mine"]):
+            k = int(ticket["cnt_host"][j])
+            out[b] = ticket["pts_host"][j, :k].numpy().astype(np.float64)
         return out
+
+    def export_batch(self, imgs_host: Sequence[torch.Tensor], mats_unwarp: torch.Tensor, mats_fwd: torch.Tensor):
+        """Synchronous form: B host images -> list of float64 [K,3] arrays (None for images another rank owns)."""
+        return self.collect(self.submit(imgs_host, mats_unwarp, mats_fwd))
 
     def export_image(self, img_host: torch.Tensor, mats_unwarp: torch.Tensor, mats_fwd: torch.Tensor) -> np.ndarray:
         """One image -> float64 [K,3]; with several ranks only rank 0 returns the points (others None)."""
         return self.export_batch([img_host], mats_unwarp, mats_fwd)[0]
+
+    def last_heat(self, B, H, W) -> torch.Tensor:
+        buf = self._buffers(B, H, W)
+        return buf["slots"][(buf["k"] - 1) & 1]["heat"]
 
 
 def export_detector_homoAdapt_b200(config, output_dir, args=None, loader=None, net: SuperPointNet_b200 = None):
@@ -162,7 +186,7 @@ def export_detector_homoAdapt_b200(config, output_dir, args=None, loader=None, n
         if pts is None:
             continue
         if config["model"].get("subpixel", {}).get("enable", False):
-            heat = exporter._bufs[next(iter(exporter._bufs))]["heat"][0]
+            heat = exporter.last_heat(1, img.shape[-2], img.shape[-1])[0]
             pts = soft_argmax_points(heat, pts.T, 5).T
         if "scene_name" in sample:
             os.makedirs(os.path.join(save_output, sample["scene_name"][0]), exist_ok=True)

@@ -165,22 +165,34 @@ class SuperPointNet_b200(nn.Module):
     # ---- whole HA step (datasets/Coco.py:262-284 + export.py:309-310) -----------------------------------
     def ha_heatmap_sums(self, img, mats_unwarp, mats_fwd, sums=None, accumulate=False, chunk: int = 0):
         """img [H,W] cuda fp32; mats [N,3,3] (this rank's views) -> sums [2,H,W] (sum heat*mask, sum mask)."""
-        dev = img.device
         H, W = img.shape[-2:]
-        mu = mats_unwarp.to(dev, torch.float32).reshape(-1, 3, 3).contiguous()
-        mf = mats_fwd.to(dev, torch.float32).reshape(-1, 3, 3).contiguous()
-        N = mu.shape[0]
+        out = self.ha_heatmap_sums_batch(img.reshape(1, H, W), mats_unwarp, mats_fwd,
+                                         None if sums is None else sums.reshape(1, 2, H, W), accumulate, chunk)
+        return out[0]
+
+    def ha_heatmap_sums_batch(self, imgs, mats_unwarp, mats_fwd, sums=None, accumulate=False, chunk: int = 0):
+        """imgs [B,H,W] cuda fp32; mats [N,3,3] shared by the batch or [B,N,3,3] -> sums [B,2,H,W].
+        All B*N views go through the kernels in passes of at most ``chunk`` views (0 = library default)."""
+        dev = imgs.device
+        B, H, W = imgs.shape
+        shared = mats_unwarp.dim() == 3
+        mu = mats_unwarp.to(dev, torch.float32).contiguous()
+        mf = mats_fwd.to(dev, torch.float32).contiguous()
+        N = mu.shape[-3]
+        if not shared and mu.shape[0] != B:
+            raise ValueError("per-image homographies must be [B,N,3,3]")
         h = self.handle(dev)
         L = _lib.lib()
         _lib.check(L.spb_net_set_ha_chunk(h, int(chunk)), "set_ha_chunk")
-        n_ws = chunk if 0 < chunk < N else N
-        nbytes = L.spb_ha_workspace_bytes(n_ws, H, W)
+        nbytes = L.spb_ha_workspace_bytes_batch(h, B, N, H, W)
         ws = self._workspace(nbytes, dev)
         if sums is None:
-            sums = torch.empty((2, H, W), device=dev, dtype=torch.float32)
+            sums = torch.empty((B, 2, H, W), device=dev, dtype=torch.float32)
             accumulate = False
+        assert sums.is_contiguous()
         with torch.cuda.device(dev):
-            _lib.check(L.spb_ha_heatmap_sums(h, img.contiguous().data_ptr(), mu.data_ptr(), mf.data_ptr(), N, H, W,
-                                             sums.data_ptr(), int(bool(accumulate)), ws.data_ptr(), ws.numel(),
-                                             torch.cuda.current_stream().cuda_stream), "ha_heatmap_sums")
+            _lib.check(L.spb_ha_heatmap_sums_batch(h, imgs.contiguous().data_ptr(), mu.data_ptr(), mf.data_ptr(),
+                                                   int(shared), B, N, H, W, sums.data_ptr(), int(bool(accumulate)),
+                                                   ws.data_ptr(), ws.numel(),
+                                                   torch.cuda.current_stream().cuda_stream), "ha_heatmap_sums_batch")
         return sums

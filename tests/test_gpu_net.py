@@ -143,3 +143,23 @@ def test_ha_end_to_end_vs_reference_golden(golden):
     # bit-exact key-points GIVEN the reference's heat-map
     pts = getPtsFromHeatmap(torch.from_numpy(g["agg"]).cuda(), 0.015, 4).T[:600]
     assert np.array_equal(pts, g["pts"])
+
+
+@pytest.mark.parametrize("chunk", [0, 16, 5])
+def test_ha_batched_images_equal_single_image_calls(chunk):
+    """spb_ha_heatmap_sums_batch over B images (shared and per-image homography sets, several pass sizes)
+    gives the same sums as one call per image."""
+    from pytorch_superpoint_b200 import SuperPointNet_b200, make_ha_homographies
+    n = SuperPointNet_b200()
+    n.load_state_dict(O.synthetic_state_dict("gauss2", seed=2))
+    B, H, W, N = 3, 48, 64, 8
+    imgs = torch.rand(B, H, W, device="cuda", generator=torch.Generator("cuda").manual_seed(5))
+    sets = [make_ha_homographies(N, seed=30 + b) for b in range(B)]
+    mu = torch.from_numpy(np.stack([s[0] for s in sets])).cuda()
+    mf = torch.from_numpy(np.stack([s[1] for s in sets])).cuda()
+    single = torch.stack([n.ha_heatmap_sums(imgs[b], mu[b], mf[b]).clone() for b in range(B)])
+    batch = n.ha_heatmap_sums_batch(imgs, mu, mf, chunk=chunk).clone()
+    assert torch.allclose(batch, single, rtol=1e-5, atol=1e-6)
+    shared_single = torch.stack([n.ha_heatmap_sums(imgs[b], mu[0], mf[0]).clone() for b in range(B)])
+    shared_batch = n.ha_heatmap_sums_batch(imgs, mu[0], mf[0], chunk=chunk).clone()
+    assert torch.allclose(shared_batch, shared_single, rtol=1e-5, atol=1e-6)
