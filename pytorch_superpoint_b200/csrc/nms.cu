@@ -8,16 +8,21 @@
 // exactly by rounds over two bitmaps held in shared memory:
 //     phase 1  an undecided pixel with a KEPT pixel in its window becomes suppressed;
 //     phase 2  an undecided pixel that beats every other undecided pixel in its window becomes KEPT.
-// Comparisons are integer compares of (fp32 bit pattern, index), so the result is bit-exact.
-// One CTA per image (warp-ballot bitmap words, funnel-shift window extraction); survivors are
-// compacted in row-major order with their 64-bit sort key and ranked by a second, grid-wide
-// count-greater kernel (keys are unique, so rank == final position).
+// Comparisons are integer compares of (order-preserving fp32 key, index), so the result is bit-exact.
+//
+// One thread-block CLUSTER (up to 8 CTAs) per image: each CTA owns a band of rows -- its slice of the
+// two bitmaps and (when it fits) the fp32 keys of band + halo live in its shared memory; after each
+// phase the d boundary rows are pushed into the neighbours' halo rows through distributed shared
+// memory and the cluster barrier separates the phases.  Bitmap words come from warp ballots, windows
+// from funnel shifts.  Survivors are compacted with their 64-bit sort key and ranked by a second,
+// grid-wide count-greater kernel (keys are unique, so rank == final position).
 #include "common.cuh"
 
 namespace spb {
 
 constexpr int kNmsThreads = 1024;
 constexpr int kMaxDist = 15;  // window bits (2d+1) must fit a 32-bit word
+constexpr int kMaxCluster = 8;
 
 struct NmsParams {
   const float* heat;
@@ -25,6 +30,8 @@ struct NmsParams {
   float thr;
   int d, border;
   int ww;      // bitmap words per row incl. one pad word on each side
+  int rb;      // rows per band (the last band may be shorter, never shorter than d)
+  int keys_smem;
   int maxk;    // key slots per image
   unsigned long long* keys;  // [B, maxk]
   int* nkept;                // [B]
@@ -44,72 +51,121 @@ __device__ __forceinline__ unsigned window_bits(const unsigned* row, int x, int 
   return __funnelshift_r(lo, hi, s & 31) & ((2u << (2 * d)) - 1u);
 }
 
+__device__ __forceinline__ unsigned cluster_rank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ unsigned cluster_size() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_barrier() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// store a word into the same shared-memory variable of another CTA of the cluster
+__device__ __forceinline__ void dsmem_store(const void* local, unsigned rank, unsigned v) {
+  unsigned la = (unsigned)__cvta_generic_to_shared(local), ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(rank));
+  asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(ra), "r"(v) : "memory");
+}
+
 __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(NmsParams p) {
-  extern __shared__ unsigned s_bits[];
-  const int b = blockIdx.x;
-  const int H = p.H, W = p.W, d = p.d, ww = p.ww;
-  const int rows = H + 2 * d;
-  unsigned* und = s_bits;                // undecided, [rows][ww]
-  unsigned* kept = s_bits + rows * ww;   // kept
+  extern __shared__ unsigned s_dyn[];
+  __shared__ int s_flag[kMaxCluster];
+  __shared__ int s_cnt[kMaxCluster];
   __shared__ int s_scan[kNmsThreads / 32];
-  __shared__ int s_total;
+  const unsigned crank = cluster_rank(), csize = cluster_size();
+  const int b = blockIdx.x / csize;
+  const int H = p.H, W = p.W, d = p.d, ww = p.ww;
+  const int y0 = crank * p.rb, y1 = min(H, y0 + p.rb), nr = max(y1 - y0, 0);
+  const int lrows = p.rb + 2 * d;                 // local bitmap rows: [0,d) top halo, [d,d+nr) own, then bottom halo
+  unsigned* und = s_dyn;                          // [lrows][ww]
+  unsigned* kept = s_dyn + lrows * ww;
+  unsigned* keys_s = s_dyn + 2 * lrows * ww;      // [lrows][W] order-preserving keys (band + halo) when keys_smem
   const float* heat = p.heat + (long long)b * H * W;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = kNmsThreads / 32;
   const int wpr = (W + 31) >> 5;  // data words per row
-  const int ntask = H * wpr;
+  const int ntask = nr * wpr;
 
-  for (int i = tid; i < 2 * rows * ww; i += kNmsThreads) s_bits[i] = 0u;
-  __syncthreads();
+  for (int i = tid; i < 2 * lrows * ww; i += kNmsThreads) s_dyn[i] = 0u;
+  if (p.keys_smem)
+    for (int i = tid; i < lrows * W; i += kNmsThreads) {
+      const int yy = y0 - d + i / W;
+      keys_s[i] = (yy >= 0 && yy < H) ? ord_bits(__ldg(heat + (long long)yy * W + i % W)) : 0u;
+    }
+  cluster_barrier();  // every CTA of the cluster is running and has cleared its bitmaps
+
+  auto key_at = [&](int yy, int xx) -> unsigned {
+    return p.keys_smem ? keys_s[(yy - y0 + d) * W + xx] : ord_bits(__ldg(heat + (long long)yy * W + xx));
+  };
+  // push my d first / last own rows of a bitmap into the neighbours' halo rows
+  auto push_halo = [&](unsigned* bm) {
+    if (d == 0 || nr == 0) return;
+    const int n = d * ww;
+    if (crank > 0)  // my first d rows -> bottom halo of the band above (which is always a full band)
+      for (int i = tid; i < n; i += kNmsThreads) dsmem_store(bm + (d + p.rb) * ww + i, crank - 1, bm[d * ww + i]);
+    if (crank + 1 < csize && y1 < H)  // my last d rows -> top halo of the band below
+      for (int i = tid; i < n; i += kNmsThreads) dsmem_store(bm + i, crank + 1, bm[nr * ww + i]);
+  };
 
   // threshold (model_wrap.py:261): fp32 compare, NaN never passes
   for (int t = warp; t < ntask; t += nwarp) {
-    const int y = t / wpr, w = t % wpr, x = w * 32 + lane;
-    const bool c = x < W && heat[y * W + x] >= p.thr;
+    const int ly = t / wpr, w = t % wpr, x = w * 32 + lane, y = y0 + ly;
+    const bool c = x < W && heat[(long long)y * W + x] >= p.thr;
     const unsigned m = __ballot_sync(0xffffffffu, c);
-    if (lane == 0) und[(y + d) * ww + w + 1] = m;
+    if (lane == 0) und[(ly + d) * ww + w + 1] = m;
   }
   __syncthreads();
+  push_halo(und);
+  cluster_barrier();
 
   while (true) {
     // phase 1: suppress undecided pixels that see a kept pixel (a kept pixel sees itself and
     // thereby retires from the undecided set one round after it was selected)
     int any = 0;
     for (int t = warp; t < ntask; t += nwarp) {
-      const int y = t / wpr, w = t % wpr, x = w * 32 + lane;
-      const unsigned word = und[(y + d) * ww + w + 1];
+      const int ly = t / wpr, w = t % wpr, x = w * 32 + lane;
+      const unsigned word = und[(ly + d) * ww + w + 1];
       if (word == 0u) continue;
       bool still = (word >> lane) & 1u;
       if (still) {
         for (int r = 0; r <= 2 * d; ++r)
-          if (window_bits(kept + (y + r) * ww, x, d)) {
+          if (window_bits(kept + (ly + r) * ww, x, d)) {
             still = false;
             break;
           }
       }
       const unsigned m = __ballot_sync(0xffffffffu, still);
-      if (lane == 0) und[(y + d) * ww + w + 1] = m;
+      if (lane == 0) und[(ly + d) * ww + w + 1] = m;
       any |= (m != 0u);
     }
-    if (!__syncthreads_or(any)) break;
+    any = __syncthreads_or(any);
+    push_halo(und);
+    if (tid < (int)csize) dsmem_store(&s_flag[crank], tid, (unsigned)any);
+    cluster_barrier();
+    int go = 0;
+    for (unsigned i = 0; i < csize; ++i) go |= s_flag[i];
+    if (!go) break;
     // phase 2: select local winners among the undecided
     for (int t = warp; t < ntask; t += nwarp) {
-      const int y = t / wpr, w = t % wpr, x = w * 32 + lane;
-      const unsigned word = und[(y + d) * ww + w + 1];
+      const int ly = t / wpr, w = t % wpr, x = w * 32 + lane, y = y0 + ly;
+      const unsigned word = und[(ly + d) * ww + w + 1];
       if (word == 0u) continue;
       bool win = (word >> lane) & 1u;
       if (win) {
-        const unsigned mine = ord_bits(heat[y * W + x]);
+        const unsigned mine = key_at(y, x);
         for (int r = 0; r <= 2 * d && win; ++r) {
           const int yy = y + r - d;
-          unsigned bits = window_bits(und + (y + r) * ww, x, d);
+          unsigned bits = window_bits(und + (ly + r) * ww, x, d);
           if (r == d) bits &= ~(1u << d);
           while (bits) {
             const int j = __ffs(bits) - 1;
             bits &= bits - 1;
             const int xx = x - d + j;
-            const unsigned other = ord_bits(__ldg(heat + yy * W + xx));
-            const bool greater = other > mine;
-            if (greater || (other == mine && (yy < y || (yy == y && xx < x)))) {
+            const unsigned other = key_at(yy, xx);
+            if (other > mine || (other == mine && (yy < y || (yy == y && xx < x)))) {
               win = false;
               break;
             }
@@ -117,21 +173,21 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(NmsParams p) {
         }
       }
       const unsigned m = __ballot_sync(0xffffffffu, win);
-      if (lane == 0 && m) kept[(y + d) * ww + w + 1] |= m;
+      if (lane == 0 && m) kept[(ly + d) * ww + w + 1] |= m;
     }
     __syncthreads();
+    push_halo(kept);
+    cluster_barrier();
   }
 
-  // border removal AFTER suppression (model_wrap.py:274-278), row-major compaction, sort keys
+  // border removal AFTER suppression (model_wrap.py:274-278), compaction with sort keys
   int mycount = 0;
-  for (int t = warp; t < ntask; t += nwarp) {  // pass 1: count per warp
-    const int y = t / wpr, w = t % wpr, x = w * 32 + lane;
-    const bool k = ((kept[(y + d) * ww + w + 1] >> lane) & 1u) && x >= p.border && x < W - p.border &&
+  for (int t = warp; t < ntask; t += nwarp) {
+    const int ly = t / wpr, w = t % wpr, x = w * 32 + lane, y = y0 + ly;
+    const bool k = ((kept[(ly + d) * ww + w + 1] >> lane) & 1u) && x >= p.border && x < W - p.border &&
                    y >= p.border && y < H - p.border;
     mycount += __popc(__ballot_sync(0xffffffffu, k));
   }
-  // tasks are strided over warps, so a plain per-warp prefix would not be row-major; compaction
-  // order does not matter for the result (keys are unique and ranked afterwards), only counts do.
   if (lane == 0) s_scan[warp] = mycount;
   __syncthreads();
   if (tid == 0) {
@@ -141,25 +197,29 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(NmsParams p) {
       s_scan[i] = acc;
       acc += c;
     }
-    s_total = acc;
-    p.nkept[b] = acc < p.maxk ? acc : p.maxk;
+    for (unsigned i = 0; i < csize; ++i) dsmem_store(&s_cnt[crank], i, (unsigned)acc);
   }
-  __syncthreads();
-  int base = s_scan[warp];
+  cluster_barrier();
+  int cta_base = 0, total = 0;
+  for (unsigned i = 0; i < csize; ++i) {
+    if (i < crank) cta_base += s_cnt[i];
+    total += s_cnt[i];
+  }
+  if (crank == 0 && tid == 0) p.nkept[b] = total < p.maxk ? total : p.maxk;
+  int base = cta_base + s_scan[warp];
   unsigned long long* keys = p.keys + (long long)b * p.maxk;
   for (int t = warp; t < ntask; t += nwarp) {
-    const int y = t / wpr, w = t % wpr, x = w * 32 + lane;
-    const bool k = ((kept[(y + d) * ww + w + 1] >> lane) & 1u) && x >= p.border && x < W - p.border &&
+    const int ly = t / wpr, w = t % wpr, x = w * 32 + lane, y = y0 + ly;
+    const bool k = ((kept[(ly + d) * ww + w + 1] >> lane) & 1u) && x >= p.border && x < W - p.border &&
                    y >= p.border && y < H - p.border;
     const unsigned m = __ballot_sync(0xffffffffu, k);
     if (k) {
       const int slot = base + __popc(m & ((1u << lane) - 1u));
-      const float c = heat[y * W + x];
-      const unsigned bits = ord_bits(c);
-      if (slot < p.maxk) keys[slot] = ((unsigned long long)bits << 32) | (unsigned)(y * W + x);
+      if (slot < p.maxk) keys[slot] = ((unsigned long long)key_at(y, x) << 32) | (unsigned)(y * W + x);
     }
     base += __popc(m);
   }
+  cluster_barrier();  // nobody leaves while a peer may still write into its shared memory
 }
 
 // rank = number of keys greater than mine; final order = key descending
@@ -208,9 +268,17 @@ __global__ void __launch_bounds__(256) rank_scatter_kernel(const float* __restri
 static int nms_maxk(int H, int W, int d) {
   return ceil_div(H, d + 1) * ceil_div(W, d + 1);  // kept points are pairwise > d apart (Chebyshev)
 }
-static size_t nms_smem(int H, int W, int d) {
-  const int ww = ceil_div(W, 32) + 2;
-  return (size_t)2 * (H + 2 * d) * ww * sizeof(unsigned);
+
+// cluster size: the largest C <= 8 whose last band still has at least max(d,1) rows
+static int nms_cluster(int H, int d, int& rb) {
+  const int need = d > 1 ? d : 1;
+  for (int c = kMaxCluster; c >= 1; --c) {
+    rb = ceil_div(H, c);
+    const int last = H - (c - 1) * rb;
+    if (last >= need && rb >= need) return c;
+  }
+  rb = H;
+  return 1;
 }
 
 }  // namespace spb
@@ -235,12 +303,6 @@ int spb_get_pts_from_heatmap(const float* heat, int B, int H, int W, float conf_
     set_error("spb_get_pts_from_heatmap: workspace %zu < %zu bytes", ws_bytes, spb_nms_workspace_bytes(B, H, W, nms_dist));
     return SPB_ENOMEM;
   }
-  const size_t smem = nms_smem(H, W, nms_dist);
-  if (smem > 200 * 1024) {
-    set_error("spb_get_pts_from_heatmap: image %dx%d needs %zu B of bitmap shared memory (> 200 KB)", H, W, smem);
-    return SPB_EINVAL;
-  }
-  SPB_CHECK_CUDA(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   NmsParams p;
   p.heat = heat;
   p.B = B;
@@ -250,11 +312,34 @@ int spb_get_pts_from_heatmap(const float* heat, int B, int H, int W, float conf_
   p.d = nms_dist;
   p.border = border_remove;
   p.ww = ceil_div(W, 32) + 2;
+  const int C = nms_cluster(H, nms_dist, p.rb);
+  const size_t lrows = (size_t)p.rb + 2 * nms_dist;
+  const size_t bm_bytes = 2 * lrows * p.ww * sizeof(unsigned), key_bytes = lrows * W * sizeof(unsigned);
+  const size_t cap = 200 * 1024;
+  if (bm_bytes > cap) {
+    set_error("spb_get_pts_from_heatmap: image %dx%d needs %zu B of bitmap shared memory per CTA (> 200 KB)", H, W, bm_bytes);
+    return SPB_EINVAL;
+  }
+  p.keys_smem = (bm_bytes + key_bytes <= cap) ? 1 : 0;
+  const size_t smem = bm_bytes + (p.keys_smem ? key_bytes : 0);
   p.maxk = nms_maxk(H, W, nms_dist);
   p.keys = static_cast<unsigned long long*>(ws);
   p.nkept = reinterpret_cast<int*>(p.keys + (size_t)B * p.maxk);
   cudaStream_t st = as_stream(stream);
-  nms_kernel<<<B, kNmsThreads, smem, st>>>(p);
+  SPB_CHECK_CUDA(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(B * C);
+  cfg.blockDim = dim3(kNmsThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = C;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  SPB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, nms_kernel, p));
   SPB_CHECK_LAUNCH();
   dim3 grid(ceil_div(p.maxk, 256), B);
   rank_scatter_kernel<<<grid, 256, 0, st>>>(heat, H, W, p.keys, p.nkept, p.maxk, top_k, capacity, pts, counts, total);
