@@ -648,6 +648,293 @@ __global__ void __launch_bounds__(160, 4) conv1a_tc_kernel(const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------------------
+// conv1a + conv1b + 2x2 max-pool in ONE kernel (the first VGG block, 44 % of the network's FLOPs).
+// conv1a's 64-channel output never touches HBM: per 16x8 output tile, the four "stage-1" warps gather the
+// 9 taps of the 18x10 halo pixels from the fp32 view into a K=16 im2col tile, two tcgen05.mma (M128 N64 K16)
+// produce conv1a for the 180 halo pixels in TMEM, the same warps apply bias + ReLU (and zero the pixels that
+// lie outside the image -- conv1b pads conv1a's OUTPUT with zeros), pack bf16 and write the rows straight into
+// conv1b's A operand in shared memory in the SWIZZLE_128B layout the shifted-window descriptors expect.
+// conv1b then runs exactly as in conv_tc_kernel (36 MMAs, weights resident, double-buffered TMEM, pooled
+// epilogue).  Warps: 0 weight loader, 1 MMA issuer, 2..5 conv1b epilogue, 6..13 stage-1 (two warps per TMEM
+// lane quadrant, each converting one half of the 64 channels).
+// The MMA order is  conv1a(i+1), conv1b(i), conv1a(i+2), ...  so stage-1 always works one tile ahead.
+// ------------------------------------------------------------------------------------------------
+struct Conv1FusedSmem {
+  uint8_t b2[9][8192];      // conv1b weights, 9 taps x [64 rows x 128 B], SWIZZLE_128B (TMA)
+  uint8_t a2[2][23552];     // conv1b A operand: 18x10 halo pixels x 128 B, SWIZZLE_128B, written by stage-1
+  uint8_t a1[2][8192];      // conv1a im2col: 256 rows x 32 B, no-swizzle core matrices
+  uint8_t b1[2048];         // conv1a weights [64][16]
+  float patch[2][20 * 12];  // zero-padded 20x12 fp32 image patch under the halo block (rows y0-2.., cols x0-2..)
+  float bias1[64], bias2[64];
+  uint64_t bars[9 + 14];    // b_full[9], a1_full[2], acc1_full[2], acc1_empty[2], a2_full[2], a2_empty[2], acc2_full[2], acc2_empty[2]
+  uint32_t tmem_slot;
+};
+
+struct Conv1FusedArgs {
+  const float* x;               // [V,H,W] fp32 views
+  const __nv_bfloat16* w1a;     // [64][16]
+  const float *bias1, *bias2;
+  __nv_bfloat16* out;           // [V,H/2,W/2,64]
+  int V, H, W, tiles_x, tiles_y, ntiles;
+};
+
+__global__ void __launch_bounds__(448, 1) conv1_fused_kernel(const __grid_constant__ CUtensorMap tm_w2, Conv1FusedArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  Conv1FusedSmem& sm = *reinterpret_cast<Conv1FusedSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar0 = smem_u32(sm.bars);
+  auto b_full = [&](int s) { return bar0 + 8u * s; };
+  auto a1_full = [&](int s) { return bar0 + 8u * (9 + s); };
+  auto acc1_full = [&](int s) { return bar0 + 8u * (11 + s); };
+  auto acc1_empty = [&](int s) { return bar0 + 8u * (13 + s); };
+  auto a2_full = [&](int s) { return bar0 + 8u * (15 + s); };
+  auto a2_empty = [&](int s) { return bar0 + 8u * (17 + s); };
+  auto acc2_full = [&](int s) { return bar0 + 8u * (19 + s); };
+  auto acc2_empty = [&](int s) { return bar0 + 8u * (21 + s); };
+
+  if (threadIdx.x < 64) {
+    sm.bias1[threadIdx.x] = a.bias1[threadIdx.x];
+    sm.bias2[threadIdx.x] = a.bias2[threadIdx.x];
+    const uint4* src = reinterpret_cast<const uint4*>(a.w1a + threadIdx.x * 16);
+    const int n = threadIdx.x;
+    *reinterpret_cast<uint4*>(sm.b1 + (n >> 3) * 256 + (n & 7) * 16) = src[0];
+    *reinterpret_cast<uint4*>(sm.b1 + (n >> 3) * 256 + 128 + (n & 7) * 16) = src[1];
+  }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 9; ++s) mbar_init(b_full(s), 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(a1_full(s), 256);
+      mbar_init(acc1_full(s), 1);
+      mbar_init(acc1_empty(s), 8);
+      mbar_init(a2_full(s), 256);
+      mbar_init(a2_empty(s), 1);
+      mbar_init(acc2_full(s), 1);
+      mbar_init(acc2_empty(s), 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_slot)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = sm.tmem_slot;
+  // TMEM columns: conv1b accumulators [0,64) [64,128); conv1a accumulators buffer j at 128 + 128 j (two M halves)
+  const int tiles_per_view = a.tiles_x * a.tiles_y;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int tap = 0; tap < 9; ++tap) {
+        mbar_expect_tx(b_full(tap), 8192);
+        tma_load_2d(smem_u32(sm.b2[tap]), &tm_w2, b_full(tap), tap * 64, 0);
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    constexpr uint32_t idesc = make_idesc(128, 64);
+    constexpr uint64_t hi_a2 = ((uint64_t)(1280 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+    constexpr uint64_t hi_b2 = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+    const uint64_t b1desc = make_desc_noswz(smem_u32(sm.b1), 128, 256);
+    auto issue_conv1a = [&](int it) {
+      const int buf = it & 1, ph = (it >> 1) & 1;
+      mbar_wait(acc1_empty(buf), ph ^ 1);
+      mbar_wait(a1_full(buf), ph);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t a1 = smem_u32(sm.a1[buf]);
+        tc_mma(tmem_base + 128 + buf * 128, make_desc_noswz(a1, 128, 256), b1desc, idesc, 0u);
+        tc_mma(tmem_base + 128 + buf * 128 + 64, make_desc_noswz(a1 + 4096, 128, 256), b1desc, idesc, 0u);
+        tc_commit(acc1_full(buf));
+      }
+      __syncwarp();
+    };
+    int it = 0;
+    if ((int)blockIdx.x < a.ntiles) issue_conv1a(0);
+    for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x, ++it) {
+      if (t + (int)gridDim.x < a.ntiles) issue_conv1a(it + 1);
+      const int buf = it & 1, ph = (it >> 1) & 1;
+      mbar_wait(acc2_empty(buf), ph ^ 1);
+      mbar_wait(a2_full(buf), ph);
+      tc_fence_after();
+      const uint32_t a2 = smem_u32(sm.a2[buf]);
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        if (it == 0) mbar_wait(b_full(tap), 0);
+        const uint32_t tap_off = ((tap / 3) * 10 + (tap % 3)) * 128;
+        const uint64_t adesc = hi_a2 | (uint64_t)(((a2 + tap_off) >> 4) | (1u << 16));
+        const uint64_t bdesc = hi_b2 | (uint64_t)((smem_u32(sm.b2[tap]) >> 4) | (1u << 16));
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            tc_mma(tmem_base + buf * 64, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (tap | k) != 0 ? 1u : 0u);
+          if (tap == 8) {
+            tc_commit(a2_empty(buf));
+            tc_commit(acc2_full(buf));
+          }
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp >= 6) {
+    // =========================== stage 1: im2col build + conv1a epilogue into conv1b's A operand =========
+    const int sid = threadIdx.x - 192;           // 0..255
+    const int quad = warp & 3;                   // TMEM lane quadrant of this warp
+    const int chalf = (warp - 6) >> 2;           // which 32 of the 64 conv1a channels this warp converts
+    const int lrow = quad * 32 + lane;           // TMEM lane; the thread owns halo pixels lrow and lrow + 128
+    auto patch_load = [&](int t) -> float {      // element sid of the 20x12 patch of tile t (zero outside the image)
+      if (sid >= 240) return 0.f;
+      const int n = t / tiles_per_view, rem = t % tiles_per_view;
+      const int yy = (rem / a.tiles_x) * 16 - 2 + sid / 12, xx = (rem % a.tiles_x) * 8 - 2 + sid % 12;
+      return (yy >= 0 && yy < a.H && xx >= 0 && xx < a.W) ? __ldg(a.x + ((long long)n * a.H + yy) * a.W + xx) : 0.f;
+    };
+    auto build = [&](float pv, int buf) {        // patch -> K=16 im2col rows of the 180 halo pixels
+      if (sid < 240) sm.patch[buf][sid] = pv;
+      named_bar_sync(2, 256);
+      if (sid < 180) {
+        const float* pp = sm.patch[buf] + (sid / 10) * 12 + sid % 10;  // tap (0,0) of halo pixel sid
+        uint32_t pk[5];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int k0 = 2 * k, k1 = 2 * k + 1;
+          const __nv_bfloat162 hh = __floats2bfloat162_rn(pp[(k0 / 3) * 12 + k0 % 3], pp[(k1 / 3) * 12 + k1 % 3]);
+          pk[k] = *reinterpret_cast<const uint32_t*>(&hh);
+        }
+        const __nv_bfloat162 hh = __floats2bfloat162_rn(pp[2 * 12 + 2], 0.f);
+        pk[4] = *reinterpret_cast<const uint32_t*>(&hh);
+        const int h = sid >> 7, rr = sid & 127;
+        uint8_t* row = sm.a1[buf] + h * 4096 + (rr >> 3) * 256 + (rr & 7) * 16;
+        *reinterpret_cast<uint4*>(row) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        *reinterpret_cast<uint4*>(row + 128) = make_uint4(pk[4], 0, 0, 0);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive(a1_full(buf));
+    };
+    int it = 0;
+    float pv = 0.f;
+    if ((int)blockIdx.x < a.ntiles) {
+      build(patch_load(blockIdx.x), 0);
+      if ((int)(blockIdx.x + gridDim.x) < a.ntiles) pv = patch_load(blockIdx.x + gridDim.x);
+    }
+    for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x, ++it) {
+      if (t + (int)gridDim.x < a.ntiles) {
+        build(pv, (it + 1) & 1);                                                   // im2col of tile it+1
+        if (t + 2 * (int)gridDim.x < a.ntiles) pv = patch_load(t + 2 * gridDim.x);  // prefetch for tile it+2
+      }
+      const int buf = it & 1, ph = (it >> 1) & 1;
+      const int rem = t % tiles_per_view;
+      const int y0 = (rem / a.tiles_x) * 16, x0 = (rem % a.tiles_x) * 8;
+      mbar_wait(acc1_full(buf), ph);
+      mbar_wait(a2_empty(buf), ph ^ 1);
+      tc_fence_after();
+      uint32_t v[2][32];
+      const uint32_t taddr = tmem_base + 128 + buf * 128 + chalf * 32 + ((uint32_t)(quad * 32) << 16);
+      tc_ld_nowait<32>(taddr, v[0]);        // halo pixels lrow        (M half 0)
+      tc_ld_nowait<32>(taddr + 64, v[1]);   // halo pixels lrow + 128  (M half 1)
+      tc_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc1_empty(buf));
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int p = h * 128 + lrow;
+        if (p < 180) {
+          const int py = y0 - 1 + p / 10, px = x0 - 1 + p % 10;
+          const bool inside = py >= 0 && py < a.H && px >= 0 && px < a.W;  // conv1b zero-pads conv1a's OUTPUT
+          uint8_t* srow = sm.a2[buf] + p * 128;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            const float4 b0 = *reinterpret_cast<const float4*>(sm.bias1 + chalf * 32 + j);
+            const float4 b1 = *reinterpret_cast<const float4*>(sm.bias1 + chalf * 32 + j + 4);
+            float f[8] = {__uint_as_float(v[h][j]) + b0.x,     __uint_as_float(v[h][j + 1]) + b0.y,
+                          __uint_as_float(v[h][j + 2]) + b0.z, __uint_as_float(v[h][j + 3]) + b0.w,
+                          __uint_as_float(v[h][j + 4]) + b1.x, __uint_as_float(v[h][j + 5]) + b1.y,
+                          __uint_as_float(v[h][j + 6]) + b1.z, __uint_as_float(v[h][j + 7]) + b1.w};
+            uint32_t pk[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const __nv_bfloat162 hh = __floats2bfloat162_rn(inside ? fmaxf(f[2 * q], 0.f) : 0.f,
+                                                              inside ? fmaxf(f[2 * q + 1], 0.f) : 0.f);
+              pk[q] = *reinterpret_cast<const uint32_t*>(&hh);
+            }
+            const int chunk = (chalf * 4 + j / 8) ^ (p & 7);  // SWIZZLE_128B
+            *reinterpret_cast<uint4*>(srow + chunk * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          }
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive(a2_full(buf));
+    }
+  } else {
+    // =========================== conv1b epilogue (warps 2..5): bias + ReLU + 2x2 max-pool + bf16 ===========
+    const int quad = warp & 3;
+    const int m = quad * 32 + lane, py = m >> 3, px = m & 7;
+    int it = 0;
+    for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x, ++it) {
+      const int buf = it & 1, ph = (it >> 1) & 1;
+      const int n = t / tiles_per_view, rem = t % tiles_per_view;
+      const int y = (rem / a.tiles_x) * 16 + py, x = (rem % a.tiles_x) * 8 + px;
+      mbar_wait(acc2_full(buf), ph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + buf * 64 + ((uint32_t)(quad * 32) << 16);
+      const bool valid = y < a.H && x < a.W && !(px & 1) && !(py & 1);
+      const long long opix = ((long long)n * (a.H >> 1) + (y >> 1)) * (a.W >> 1) + (x >> 1);
+      uint32_t v[2][32];
+      tc_ld_nowait<32>(taddr, v[0]);
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        tc_wait_ld();
+        if (b == 0) {
+          tc_ld_nowait<32>(taddr + 32, v[1]);
+        } else {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(acc2_empty(buf));
+        }
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 bb = *reinterpret_cast<const float4*>(sm.bias2 + b * 32 + j);
+          f[j] = __uint_as_float(v[b][j]) + bb.x;
+          f[j + 1] = __uint_as_float(v[b][j + 1]) + bb.y;
+          f[j + 2] = __uint_as_float(v[b][j + 2]) + bb.z;
+          f[j + 3] = __uint_as_float(v[b][j + 3]) + bb.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          f[j] = fmaxf(f[j], 0.f);
+          f[j] = fmaxf(f[j], __shfl_xor_sync(0xffffffffu, f[j], 1));
+          f[j] = fmaxf(f[j], __shfl_xor_sync(0xffffffffu, f[j], 8));
+        }
+        if (valid) {
+          __nv_bfloat16* o = a.out + opix * 64 + b * 32;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const __nv_bfloat162 hh = __floats2bfloat162_rn(f[j + 2 * q], f[j + 2 * q + 1]);
+              pk[q] = *reinterpret_cast<const uint32_t*>(&hh);
+            }
+            *reinterpret_cast<uint4*>(o + j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -733,6 +1020,41 @@ int conv1a_tc(const LayerDev& L, const float* x, __nv_bfloat16* out, int B, int 
   int grid = kNumSMs * 4;
   if (grid > ntiles) grid = ntiles;
   conv1a_tc_kernel<<<grid, 160, smem, st>>>(tm, x, L.w_tc, L.bias, npix, H, W, ntiles);
+  SPB_CHECK_LAUNCH();
+  return SPB_OK;
+}
+
+static int g_fuse1 = 1;  // conv1a fused into conv1b's kernel (0: two kernels, for A/B tests)
+extern "C" int spb_conv_tc_set_fuse1(int on) {
+  g_fuse1 = on ? 1 : 0;
+  return SPB_OK;
+}
+bool conv1_fused_enabled() { return g_fuse1 != 0; }
+
+int conv1_fused(const LayerDev& L1a, const LayerDev& L1b, const float* x, __nv_bfloat16* out, int V, int H, int W,
+                cudaStream_t st) {
+  if ((H | W) & 1) {
+    set_error("conv1_fused: pooled block needs even H, W (got %dx%d)", H, W);
+    return SPB_EINVAL;
+  }
+  CUtensorMap tm_w2;
+  memcpy(&tm_w2, L1b.tmap_w, sizeof(tm_w2));
+  Conv1FusedArgs a;
+  a.x = x;
+  a.w1a = L1a.w_tc;
+  a.bias1 = L1a.bias;
+  a.bias2 = L1b.bias;
+  a.out = out;
+  a.V = V;
+  a.H = H;
+  a.W = W;
+  a.tiles_x = ceil_div(W, 8);
+  a.tiles_y = ceil_div(H, 16);
+  a.ntiles = V * a.tiles_x * a.tiles_y;
+  const int smem = (int)sizeof(Conv1FusedSmem) + 1024;
+  SPB_CHECK_CUDA(cudaFuncSetAttribute(conv1_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int grid = a.ntiles < kNumSMs ? a.ntiles : kNumSMs;
+  conv1_fused_kernel<<<grid, 448, smem, st>>>(tm_w2, a);
   SPB_CHECK_LAUNCH();
   return SPB_OK;
 }

@@ -105,8 +105,14 @@ static int forward(const Net* net, const float* x, int B, int H, int W, float* s
   int rc;
 #define RUN(li, in, out, h, wd, mode)                                     \
   if ((rc = run_layer(net, li, in, out, B, h, wd, mode, st)) != SPB_OK) return rc
-  RUN(0, x, w.buf0, H, W, 0);
-  RUN(1, w.buf0, w.buf1, H, W, 0);  // + pool -> H/2
+  if (net->impl == SPB_IMPL_TCGEN05 && conv1_fused_enabled()) {
+    // conv1a + conv1b + pool in one kernel: the 64-channel full-resolution activation never leaves the SM
+    StageTimer tm(net, 1, st);
+    if ((rc = conv1_fused(net->layer[0], net->layer[1], x, w.buf1, B, H, W, st)) != SPB_OK) return rc;
+  } else {
+    RUN(0, x, w.buf0, H, W, 0);
+    RUN(1, w.buf0, w.buf1, H, W, 0);  // + pool -> H/2
+  }
   RUN(2, w.buf1, w.buf0, H / 2, W / 2, 0);
   RUN(3, w.buf0, w.buf1, H / 2, W / 2, 0);  // + pool -> H/4
   RUN(4, w.buf1, w.buf0, H / 4, W / 4, 0);

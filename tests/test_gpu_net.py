@@ -163,3 +163,23 @@ def test_ha_batched_images_equal_single_image_calls(chunk):
     shared_single = torch.stack([n.ha_heatmap_sums(imgs[b], mu[0], mf[0]).clone() for b in range(B)])
     shared_batch = n.ha_heatmap_sums_batch(imgs, mu[0], mf[0], chunk=chunk).clone()
     assert torch.allclose(shared_batch, shared_single, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("B,H,W", [(1, 16, 8), (2, 24, 40), (3, 64, 96), (2, 240, 320), (1, 40, 24)])
+def test_conv1_fused_block_equals_two_kernels(net, B, H, W):
+    """conv1a+conv1b+pool fused in one kernel (conv1a's output stays in shared memory) == the two-kernel path."""
+    from pytorch_superpoint_b200 import _lib
+    L = _lib.lib()
+    x = torch.rand(B, 1, H, W, device="cuda", generator=torch.Generator("cuda").manual_seed(W))
+    net.set_impl("tcgen05")
+    try:
+        L.spb_conv_tc_set_fuse1(0)
+        s0, d0 = net.forward_nhwc(x)
+        s0, d0 = s0.clone(), d0.clone()
+        L.spb_conv_tc_set_fuse1(1)
+        s1, d1 = net.forward_nhwc(x)
+    finally:
+        L.spb_conv_tc_set_fuse1(1)
+    assert torch.isfinite(s1).all()
+    assert (s0 - s1).abs().max().item() <= 1e-5  # same bf16 intermediate, same accumulation order
+    assert (d0 - d1).abs().max().item() <= 1e-6

@@ -23,12 +23,29 @@ ap.add_argument("--w", type=int, default=320)
 ap.add_argument("--halo", type=int, default=1)
 ap.add_argument("--iters", type=int, default=5)
 ap.add_argument("--impl", default="tcgen05")
+ap.add_argument("--forward", action="store_true", help="run the whole detector forward instead of one layer")
+ap.add_argument("--fuse1", type=int, default=1)
 a = ap.parse_args()
 L = _lib.lib()
 net = SuperPointNet_b200(impl=a.impl)
 net.load_state_dict(synthetic_state_dict("gauss2", 1))
 h = net.handle(torch.device("cuda", 0))
 L.spb_conv_tc_set_halo(a.halo)
+L.spb_conv_tc_set_fuse1(a.fuse1)
+if a.forward:
+    x = torch.rand(a.views, 1, a.h, a.w, device="cuda")
+    for _ in range(2):
+        net.forward_nhwc(x, want_desc=False)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.iters):
+        net.forward_nhwc(x, want_desc=False)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / a.iters
+    print(f"forward views {a.views} {a.h}x{a.w} fuse1={a.fuse1}: {ms:.4f} ms  {12.161e-3 * a.views / ms * (a.h * a.w) / 76800:.1f} TFLOP/s")
+    sys.exit(0)
 cin, cout, ks = SHAPES[a.layer]
 if a.layer == 0:
     x = torch.rand(a.views, a.h, a.w, device="cuda")
