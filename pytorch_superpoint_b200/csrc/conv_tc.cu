@@ -498,6 +498,13 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// two fp32 accumulators -> ReLU -> packed bf16x2 (pack first, then one packed max)
+__device__ __forceinline__ uint32_t relu_pack_bf16(uint32_t a, uint32_t b) {
+  const __nv_bfloat162 h = __hmax2(__floats2bfloat162_rn(__uint_as_float(a), __uint_as_float(b)),
+                                   __floats2bfloat162_rn(0.f, 0.f));
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
 struct Conv1aSmem {
   uint8_t stage[2][16384];  // output tiles, 128 rows x 128 B, SWIZZLE_128B (TMA store source)
   uint8_t a[2][4096];       // im2col tiles
@@ -581,12 +588,12 @@ __global__ void __launch_bounds__(160, 4) conv1a_tc_kernel(const __grid_constant
           const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
           pk[k] = *reinterpret_cast<const uint32_t*>(&h);
         }
-        const __nv_bfloat162 h = __floats2bfloat162_rn(v[8], 0.f);
+        const __nv_bfloat162 h = __floats2bfloat162_rn(v[8], 1.f);  // slot 9 = 1: bias head (folded into the MMA)
         pk[4] = *reinterpret_cast<const uint32_t*>(&h);
       }
       uint8_t* row = sm.a[buf] + (r >> 3) * 256 + (r & 7) * 16;
       *reinterpret_cast<uint4*>(row) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-      *reinterpret_cast<uint4*>(row + 128) = make_uint4(pk[4], 0, 0, 0);
+      *reinterpret_cast<uint4*>(row + 128) = make_uint4(pk[4], p < npix ? 0x00003F80u : 0u, 0, 0);  // slot 10 = 1: bias tail
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       mbar_arrive(a_full(buf));
     };
@@ -614,20 +621,11 @@ __global__ void __launch_bounds__(160, 4) conv1a_tc_kernel(const __grid_constant
         }
 #pragma unroll
         for (int j = 0; j < 32; j += 8) {
-          const float4 b0 = *reinterpret_cast<const float4*>(sm.bias + b * 32 + j);
-          const float4 b1 = *reinterpret_cast<const float4*>(sm.bias + b * 32 + j + 4);
-          const __nv_bfloat162 h0 = __floats2bfloat162_rn(fmaxf(__uint_as_float(v[j]) + b0.x, 0.f),
-                                                          fmaxf(__uint_as_float(v[j + 1]) + b0.y, 0.f));
-          const __nv_bfloat162 h1 = __floats2bfloat162_rn(fmaxf(__uint_as_float(v[j + 2]) + b0.z, 0.f),
-                                                          fmaxf(__uint_as_float(v[j + 3]) + b0.w, 0.f));
-          const __nv_bfloat162 h2 = __floats2bfloat162_rn(fmaxf(__uint_as_float(v[j + 4]) + b1.x, 0.f),
-                                                          fmaxf(__uint_as_float(v[j + 5]) + b1.y, 0.f));
-          const __nv_bfloat162 h3 = __floats2bfloat162_rn(fmaxf(__uint_as_float(v[j + 6]) + b1.z, 0.f),
-                                                          fmaxf(__uint_as_float(v[j + 7]) + b1.w, 0.f));
+          uint32_t pk[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) pk[q] = relu_pack_bf16(v[j + 2 * q], v[j + 2 * q + 1]);  // bias is in the MMA
           const int chunk = (b * 4 + j / 8) ^ (r & 7);  // SWIZZLE_128B: 16-byte chunk XOR (row mod 8)
-          *reinterpret_cast<uint4*>(srow + chunk * 16) =
-              make_uint4(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1),
-                         *reinterpret_cast<const uint32_t*>(&h2), *reinterpret_cast<const uint32_t*>(&h3));
+          *reinterpret_cast<uint4*>(srow + chunk * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -792,11 +790,16 @@ __global__ void __launch_bounds__(448, 1) conv1_fused_kernel(const __grid_consta
       const int yy = (rem / a.tiles_x) * 16 - 2 + sid / 12, xx = (rem % a.tiles_x) * 8 - 2 + sid % 12;
       return (yy >= 0 && yy < a.H && xx >= 0 && xx < a.W) ? __ldg(a.x + ((long long)n * a.H + yy) * a.W + xx) : 0.f;
     };
-    auto build = [&](float pv, int buf) {        // patch -> K=16 im2col rows of the 180 halo pixels
+    auto build = [&](float pv, int t, int buf) {  // patch -> K=16 im2col rows of the 180 halo pixels of tile t
+      const int y0 = ((t % tiles_per_view) / a.tiles_x) * 16, x0 = ((t % tiles_per_view) % a.tiles_x) * 8;
       if (sid < 240) sm.patch[buf][sid] = pv;
       named_bar_sync(2, 256);
       if (sid < 180) {
         const float* pp = sm.patch[buf] + (sid / 10) * 12 + sid % 10;  // tap (0,0) of halo pixel sid
+        // conv1b zero-pads conv1a's OUTPUT: a halo pixel outside the image must come out as exactly 0, so its
+        // whole im2col row is zeroed (its taps can reach inside the image), INCLUDING the two bias slots
+        const int hy = y0 - 1 + sid / 10, hx = x0 - 1 + sid % 10;
+        const bool inside = hy >= 0 && hy < a.H && hx >= 0 && hx < a.W;
         uint32_t pk[5];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -804,12 +807,13 @@ __global__ void __launch_bounds__(448, 1) conv1_fused_kernel(const __grid_consta
           const __nv_bfloat162 hh = __floats2bfloat162_rn(pp[(k0 / 3) * 12 + k0 % 3], pp[(k1 / 3) * 12 + k1 % 3]);
           pk[k] = *reinterpret_cast<const uint32_t*>(&hh);
         }
-        const __nv_bfloat162 hh = __floats2bfloat162_rn(pp[2 * 12 + 2], 0.f);
+        const __nv_bfloat162 hh = __floats2bfloat162_rn(pp[2 * 12 + 2], 1.f);  // slot 9: bias head
         pk[4] = *reinterpret_cast<const uint32_t*>(&hh);
+        if (!inside) pk[0] = pk[1] = pk[2] = pk[3] = pk[4] = 0u;
         const int h = sid >> 7, rr = sid & 127;
         uint8_t* row = sm.a1[buf] + h * 4096 + (rr >> 3) * 256 + (rr & 7) * 16;
         *reinterpret_cast<uint4*>(row) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        *reinterpret_cast<uint4*>(row + 128) = make_uint4(pk[4], 0, 0, 0);
+        *reinterpret_cast<uint4*>(row + 128) = make_uint4(pk[4], inside ? 0x00003F80u : 0u, 0, 0);  // slot 10: bias tail
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       mbar_arrive(a1_full(buf));
@@ -817,17 +821,15 @@ __global__ void __launch_bounds__(448, 1) conv1_fused_kernel(const __grid_consta
     int it = 0;
     float pv = 0.f;
     if ((int)blockIdx.x < a.ntiles) {
-      build(patch_load(blockIdx.x), 0);
+      build(patch_load(blockIdx.x), blockIdx.x, 0);
       if ((int)(blockIdx.x + gridDim.x) < a.ntiles) pv = patch_load(blockIdx.x + gridDim.x);
     }
     for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x, ++it) {
       if (t + (int)gridDim.x < a.ntiles) {
-        build(pv, (it + 1) & 1);                                                   // im2col of tile it+1
+        build(pv, t + gridDim.x, (it + 1) & 1);                                    // im2col of tile it+1
         if (t + 2 * (int)gridDim.x < a.ntiles) pv = patch_load(t + 2 * gridDim.x);  // prefetch for tile it+2
       }
       const int buf = it & 1, ph = (it >> 1) & 1;
-      const int rem = t % tiles_per_view;
-      const int y0 = (rem / a.tiles_x) * 16, x0 = (rem % a.tiles_x) * 8;
       mbar_wait(acc1_full(buf), ph);
       mbar_wait(a2_empty(buf), ph ^ 1);
       tc_fence_after();
@@ -842,25 +844,13 @@ __global__ void __launch_bounds__(448, 1) conv1_fused_kernel(const __grid_consta
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int p = h * 128 + lrow;
-        if (p < 180) {
-          const int py = y0 - 1 + p / 10, px = x0 - 1 + p % 10;
-          const bool inside = py >= 0 && py < a.H && px >= 0 && px < a.W;  // conv1b zero-pads conv1a's OUTPUT
+        if (p < 180) {  // bias and the out-of-image zeroing are already in the accumulator (see build)
           uint8_t* srow = sm.a2[buf] + p * 128;
 #pragma unroll
           for (int j = 0; j < 32; j += 8) {
-            const float4 b0 = *reinterpret_cast<const float4*>(sm.bias1 + chalf * 32 + j);
-            const float4 b1 = *reinterpret_cast<const float4*>(sm.bias1 + chalf * 32 + j + 4);
-            float f[8] = {__uint_as_float(v[h][j]) + b0.x,     __uint_as_float(v[h][j + 1]) + b0.y,
-                          __uint_as_float(v[h][j + 2]) + b0.z, __uint_as_float(v[h][j + 3]) + b0.w,
-                          __uint_as_float(v[h][j + 4]) + b1.x, __uint_as_float(v[h][j + 5]) + b1.y,
-                          __uint_as_float(v[h][j + 6]) + b1.z, __uint_as_float(v[h][j + 7]) + b1.w};
             uint32_t pk[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const __nv_bfloat162 hh = __floats2bfloat162_rn(inside ? fmaxf(f[2 * q], 0.f) : 0.f,
-                                                              inside ? fmaxf(f[2 * q + 1], 0.f) : 0.f);
-              pk[q] = *reinterpret_cast<const uint32_t*>(&hh);
-            }
+            for (int q = 0; q < 4; ++q) pk[q] = relu_pack_bf16(v[h][j + 2 * q], v[h][j + 2 * q + 1]);
             const int chunk = (chalf * 4 + j / 8) ^ (p & 7);  // SWIZZLE_128B
             *reinterpret_cast<uint4*>(srow + chunk * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           }

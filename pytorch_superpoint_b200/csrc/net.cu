@@ -187,6 +187,15 @@ int spb_net_create(spb_net** out, const float* const* weights, const float* cons
           wt[(size_t)co * Kpad + (size_t)t * S.cin + ci] = v;
         }
     }
+    if (li == 0) {
+      // tensor-core conv1a folds its bias into the MMA: im2col slots 9 and 10 carry the constant 1 and the
+      // weight rows carry the bias split into a bf16 head and a bf16 residual (fp32-accurate to ~2^-17)
+      for (int co = 0; co < S.cout; ++co) {
+        const __nv_bfloat16 hi = __float2bfloat16_rn(b[co]);
+        wt[(size_t)co * Kpad + 9] = hi;
+        wt[(size_t)co * Kpad + 10] = __float2bfloat16_rn(b[co] - __bfloat162float(hi));
+      }
+    }
     SPB_CHECK_CUDA(cudaMalloc(&L.bias, b.size() * sizeof(float)));
     SPB_CHECK_CUDA(cudaMemcpy(L.bias, b.data(), b.size() * sizeof(float), cudaMemcpyHostToDevice));
     SPB_CHECK_CUDA(cudaMalloc(&L.w_simt, ws.size() * 2));

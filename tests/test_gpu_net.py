@@ -111,6 +111,10 @@ def test_forward_vs_reference_golden(impl, layout, golden):
     assert (heat - ref_heat).abs().max().item() < 1e-2          # north_star: max-abs 1e-2 heat-map in bf16
     cos = (desc * ref_desc).sum(1)
     assert cos.min().item() > 0.999                              # north_star: descriptor cosine >= 0.999
+    # what bf16 activations/weights with fp32 accumulation actually deliver on this input (CPU emulation:
+    # cos >= 0.99996, |semi| error <= 0.015): anything worse is a kernel bug, not rounding
+    assert cos.min().item() > 0.9999
+    assert (semi - ref_semi).abs().max().item() < 0.03
     assert (desc.norm(dim=1) - 1).abs().max().item() < 1e-4
 
 
