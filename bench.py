@@ -11,7 +11,8 @@ over ranks) -> divide -> threshold + greedy NMS + top-600.  Rank 0 prints ONE JS
 
   value      images/s with inputs resident in HBM (CUDA events, barrier + synchronize both sides, max over ranks)
   e2e        same metric through HAExporter.export_batch with pinned HOST images in and HOST key-points out
-  roofline   the dominant kernel (conv_tc 64->64 3x3: conv1b) against the measured bf16 tensor peak
+  roofline   the dominant kernel (conv1_fused_kernel: conv1a+conv1b+pool, 44 % of the conv FLOPs) against the
+             measured bf16 tensor peak
   cpu_baseline  the CPU oracle port of the reference path on this box's host cores (rank 0, N=1 only)
   --impl reference   times that CPU arm as the main line (bounded sample per step)
 """
@@ -38,6 +39,7 @@ UNIT = "images/s"
 WORKLOAD = ("HA export: 100 homographies x 240x320 (configs[1], magicpoint_coco_export.yaml shape); "
             "SuperPointNet_gauss2 weights, seeded random init, eval-mode BN folded; thr 0.015, nms 4, top_k 600")
 CONV_GFLOP_DET = 12.161  # conv FLOPs per 240x320 view, detector path only
+TRAFFIC_BYTES_PER_VIEW = None  # filled from profiles/r01_ncu_conv1_fused.txt (dram read+write per view)
 
 
 def structured_images(n, seed=0):
@@ -75,7 +77,7 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -247,7 +249,7 @@ def run_b200(args):
     # ---- roofline of the dominant kernel: a profiled pass (CUDA events around every stage launch) -------
     h = net.handle(dev)
     _lib.check(L.spb_net_profile(h, 1))
-    prof_steps = min(args.steps, 5)
+    prof_steps = min(args.steps, 10)
     ms_prof = timed(step_resident, prof_steps)
     import ctypes as C
     st_ms, st_n = (C.c_float * 16)(), (C.c_int * 16)()
@@ -260,14 +262,21 @@ def run_b200(args):
     lo, hi = shard_bounds(NVIEWS, rank, world)
     views_local = hi - lo
     peak_tf, peak_hbm, peak_src = peaks()
+    # stage 1 = conv1_fused_kernel: conv1a (1->64) + conv1b (64->64) + pool in one launch
     k_launches = st_n[1]
     k_ms = st_ms[1] / max(k_launches, 1)
-    flop_per_launch = 2.0 * H * W * 64 * 64 * 9 * (B * views_local * prof_steps / max(k_launches, 1))
+    views_per_launch = B * views_local * prof_steps / max(k_launches, 1)
+    flop_per_launch = 2.0 * H * W * 64 * 9 * (64 + 1) * views_per_launch
     achieved = flop_per_launch / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
     net_ms = sum(st_ms[i] for i in range(12)) / prof_steps
-    roofline = {"bound": "tensor", "kernel": "conv_tc_kernel<Cin64,Cout64,3x3,halo> (conv1b: 43.5% of conv FLOPs)",
+    # DRAM traffic of that kernel from the ncu --set full capture in profiles/ (bytes per view, measured at
+    # 100 views per launch), scaled to this run's views per launch
+    traffic = TRAFFIC_BYTES_PER_VIEW * views_per_launch if TRAFFIC_BYTES_PER_VIEW else None
+    roofline = {"bound": "tensor", "kernel": "conv1_fused_kernel (conv1a+conv1b+pool: 44.2% of the detector's conv FLOPs)",
                 "achieved": round(achieved, 2), "peak": peak_tf, "unit": "TFLOP/s", "frac": round(achieved / peak_tf, 4),
-                "traffic": None, "peak_source": peak_src, "avg_launch_ms": round(k_ms, 4), "launches": int(k_launches),
+                "traffic": traffic, "algorithmic_bytes": (H * W * 4 + (H // 2) * (W // 2) * 64 * 2) * views_per_launch,
+                "peak_source": peak_src, "avg_launch_ms": round(k_ms, 4), "launches": int(k_launches),
+                "views_per_launch": views_per_launch,
                 "whole_net_tflops": round(CONV_GFLOP_DET * 1e-3 * B * views_local / (net_ms * 1e-3), 2) if net_ms else None}
 
     line = {"metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -313,7 +322,7 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--images", type=int, default=8, help="images per step")

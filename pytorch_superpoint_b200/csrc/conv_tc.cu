@@ -114,6 +114,40 @@ __device__ __forceinline__ void tc_ld_nowait<32>(uint32_t taddr, uint32_t (&v)[3
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// 32 fp32 accumulator columns of one pixel -> + bias -> bf16x2 pack -> ReLU -> optional 2x2 max-pool with PACKED
+// lane shuffles (lane = 4 tile rows x 8 tile columns: partners are lane^1 and lane^8; max commutes with the
+// monotone bf16 rounding, so pooling after the pack is exact) -> one 64-byte store by the lane that owns the output.
+template <bool POOL>
+__device__ __forceinline__ void epi_bf16_32(const uint32_t (&v)[32], const float* __restrict__ bias, bool valid,
+                                            __nv_bfloat16* __restrict__ o) {
+  uint32_t pk[16];
+  const __nv_bfloat162 zero = __floats2bfloat162_rn(0.f, 0.f);
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    const float4 bb = *reinterpret_cast<const float4*>(bias + j);
+    __nv_bfloat162 h0 = __hmax2(__floats2bfloat162_rn(__uint_as_float(v[j]) + bb.x, __uint_as_float(v[j + 1]) + bb.y), zero);
+    __nv_bfloat162 h1 = __hmax2(__floats2bfloat162_rn(__uint_as_float(v[j + 2]) + bb.z, __uint_as_float(v[j + 3]) + bb.w), zero);
+    uint32_t u0 = *reinterpret_cast<const uint32_t*>(&h0), u1 = *reinterpret_cast<const uint32_t*>(&h1);
+    if (POOL) {
+#pragma unroll
+      for (int sh = 1; sh <= 8; sh <<= 3) {
+        const uint32_t p0 = __shfl_xor_sync(0xffffffffu, u0, sh), p1 = __shfl_xor_sync(0xffffffffu, u1, sh);
+        h0 = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&u0), *reinterpret_cast<const __nv_bfloat162*>(&p0));
+        h1 = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&u1), *reinterpret_cast<const __nv_bfloat162*>(&p1));
+        u0 = *reinterpret_cast<const uint32_t*>(&h0);
+        u1 = *reinterpret_cast<const uint32_t*>(&h1);
+      }
+    }
+    pk[j / 2] = u0;
+    pk[j / 2 + 1] = u1;
+  }
+  if (valid) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      *reinterpret_cast<uint4*>(o + q * 8) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+  }
+}
+
 // K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
 // [0,14) start>>4, [16,30) LBO>>4 (unused for swizzled K-major), [32,46) SBO>>4, [46,48) version=1,
 // [61,64) layout (2 = SWIZZLE_128B).
@@ -136,6 +170,8 @@ struct ConvCfg {
   static constexpr int CIN = CIN_, NPAD = NPAD_, KS = KS_, NA = NA_, OUT = OUT_;
   static constexpr bool POOL = POOL_;
   static constexpr int BW = (NPAD_ % 32 == 0) ? 32 : 16;  // TMEM columns per epilogue batch
+  static constexpr int EPI_WARPS = OUT_ == 0 ? 8 : 4;     // bf16 layers: two warps per TMEM lane quadrant, half the columns each
+  static constexpr int THREADS = 64 + 32 * EPI_WARPS;
   static constexpr int STAGE_BYTES = OUT_ == 1 ? 4 * 32 * 65 * 4 : 0;
   static constexpr bool HALO = HALO_ && KS_ > 1, BRES = BRES_;
   static constexpr int TAPS = KS * KS, CHUNKS = CIN / 64;
@@ -164,7 +200,7 @@ struct ConvArgs {
 };
 
 template <class C>
-__global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act,
+__global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act,
                                                          const __grid_constant__ CUtensorMap tm_wgt, ConvArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space
@@ -196,7 +232,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(acc_full(s), 1);
-      mbar_init(acc_empty(s), 4);
+      mbar_init(acc_empty(s), C::EPI_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -310,13 +346,15 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
       if (++as == 2) { as = 0; pacc ^= 1; }
     }
   } else {
-    // =========================== epilogue (warps 2..5) ===========================
+    // =========================== epilogue (warps 2..5, or 2..9 for the bf16 layers) ===========================
     // TMEM -> registers in batches of BW columns, software pipelined (the next batch's tcgen05.ld is in
     // flight while this one is processed); the accumulator is handed back to the MMA warp as soon as the
     // last batch has landed in registers.
     const int quad = warp & 3;  // TMEM lane quadrant this warp may read
     const int m = quad * 32 + lane, py = m >> 3, px = m & 7;
-    constexpr int BW = C::BW, NBATCH = C::NPAD / BW;
+    constexpr int COLS = C::NPAD / (C::EPI_WARPS / 4);  // accumulator columns this warp converts
+    constexpr int BW = C::BW, NBATCH = COLS / BW;
+    const int col0 = ((warp - 2) >> 2) * COLS;
     int as = 0, pacc = 0;
     for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x) {
       const int n = t / (a.tiles_x * a.tiles_y), rem = t % (a.tiles_x * a.tiles_y);
@@ -384,18 +422,22 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
         continue;
       }
       uint32_t v[2][BW];
-      tc_ld_nowait<BW>(taddr, v[0]);
+      tc_ld_nowait<BW>(taddr + col0, v[0]);
 #pragma unroll
       for (int b = 0; b < NBATCH; ++b) {
         tc_wait_ld();
         if (b + 1 < NBATCH) {
-          tc_ld_nowait<BW>(taddr + (b + 1) * BW, v[(b + 1) & 1]);
+          tc_ld_nowait<BW>(taddr + col0 + (b + 1) * BW, v[(b + 1) & 1]);
         } else {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(acc_empty(as));
         }
-        const int c0 = b * BW;
+        const int c0 = col0 + b * BW;
+        if constexpr (C::OUT == 0) {
+          epi_bf16_32<C::POOL>(v[b & 1], sBias + c0, valid, static_cast<__nv_bfloat16*>(a.out) + opix * a.cout + c0);
+          continue;
+        }
         float f[BW];
 #pragma unroll
         for (int j = 0; j < BW; j += 4) {
@@ -653,8 +695,8 @@ __global__ void __launch_bounds__(160, 4) conv1a_tc_kernel(const __grid_constant
 // lie outside the image -- conv1b pads conv1a's OUTPUT with zeros), pack bf16 and write the rows straight into
 // conv1b's A operand in shared memory in the SWIZZLE_128B layout the shifted-window descriptors expect.
 // conv1b then runs exactly as in conv_tc_kernel (36 MMAs, weights resident, double-buffered TMEM, pooled
-// epilogue).  Warps: 0 weight loader, 1 MMA issuer, 2..5 conv1b epilogue, 6..13 stage-1 (two warps per TMEM
-// lane quadrant, each converting one half of the 64 channels).
+// epilogue).  Warps: 0 weight loader, 1 MMA issuer, 2..9 conv1b epilogue, 10..17 stage-1 (in both groups two
+// warps share a TMEM lane quadrant, each converting one half of the 64 channels).
 // The MMA order is  conv1a(i+1), conv1b(i), conv1a(i+2), ...  so stage-1 always works one tile ahead.
 // ------------------------------------------------------------------------------------------------
 struct Conv1FusedSmem {
@@ -674,9 +716,10 @@ struct Conv1FusedArgs {
   const float *bias1, *bias2;
   __nv_bfloat16* out;           // [V,H/2,W/2,64]
   int V, H, W, tiles_x, tiles_y, ntiles;
+  long long* dbg;               // optional timeline probe (CTA 0): [64 iterations][16 slots] of clock64, or NULL
 };
 
-__global__ void __launch_bounds__(448, 1) conv1_fused_kernel(const __grid_constant__ CUtensorMap tm_w2, Conv1FusedArgs a) {
+__global__ void __launch_bounds__(576, 1) conv1_fused_kernel(const __grid_constant__ CUtensorMap tm_w2, Conv1FusedArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   Conv1FusedSmem& sm = *reinterpret_cast<Conv1FusedSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -707,7 +750,7 @@ __global__ void __launch_bounds__(448, 1) conv1_fused_kernel(const __grid_consta
       mbar_init(a2_full(s), 256);
       mbar_init(a2_empty(s), 1);
       mbar_init(acc2_full(s), 1);
-      mbar_init(acc2_empty(s), 4);
+      mbar_init(acc2_empty(s), 8);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -752,12 +795,18 @@ __global__ void __launch_bounds__(448, 1) conv1_fused_kernel(const __grid_consta
       __syncwarp();
     };
     int it = 0;
+#define SPB_PROBE(slot)                                                                       \
+  if (a.dbg && blockIdx.x == 0 && it < 64 && lane == 0) a.dbg[it * 16 + (slot)] = clock64()
     if ((int)blockIdx.x < a.ntiles) issue_conv1a(0);
     for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x, ++it) {
+      SPB_PROBE(0);
       if (t + (int)gridDim.x < a.ntiles) issue_conv1a(it + 1);
+      SPB_PROBE(1);
       const int buf = it & 1, ph = (it >> 1) & 1;
       mbar_wait(acc2_empty(buf), ph ^ 1);
+      SPB_PROBE(2);
       mbar_wait(a2_full(buf), ph);
+      SPB_PROBE(3);
       tc_fence_after();
       const uint32_t a2 = smem_u32(sm.a2[buf]);
 #pragma unroll
@@ -777,12 +826,13 @@ __global__ void __launch_bounds__(448, 1) conv1_fused_kernel(const __grid_consta
         }
         __syncwarp();
       }
+      SPB_PROBE(4);
     }
-  } else if (warp >= 6) {
+  } else if (warp >= 10) {
     // =========================== stage 1: im2col build + conv1a epilogue into conv1b's A operand =========
-    const int sid = threadIdx.x - 192;           // 0..255
+    const int sid = threadIdx.x - 320;           // 0..255
     const int quad = warp & 3;                   // TMEM lane quadrant of this warp
-    const int chalf = (warp - 6) >> 2;           // which 32 of the 64 conv1a channels this warp converts
+    const int chalf = (warp - 10) >> 2;          // which 32 of the 64 conv1a channels this warp converts
     const int lrow = quad * 32 + lane;           // TMEM lane; the thread owns halo pixels lrow and lrow + 128
     auto patch_load = [&](int t) -> float {      // element sid of the 20x12 patch of tile t (zero outside the image)
       if (sid >= 240) return 0.f;
@@ -825,13 +875,19 @@ __global__ void __launch_bounds__(448, 1) conv1_fused_kernel(const __grid_consta
       if ((int)(blockIdx.x + gridDim.x) < a.ntiles) pv = patch_load(blockIdx.x + gridDim.x);
     }
     for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x, ++it) {
+#define SPB_PROBE1(slot)                                                                                 \
+  if (a.dbg && blockIdx.x == 0 && it < 64 && threadIdx.x == 320) a.dbg[it * 16 + (slot)] = clock64()
+      SPB_PROBE1(5);
       if (t + (int)gridDim.x < a.ntiles) {
         build(pv, t + gridDim.x, (it + 1) & 1);                                    // im2col of tile it+1
         if (t + 2 * (int)gridDim.x < a.ntiles) pv = patch_load(t + 2 * gridDim.x);  // prefetch for tile it+2
       }
+      SPB_PROBE1(6);
       const int buf = it & 1, ph = (it >> 1) & 1;
       mbar_wait(acc1_full(buf), ph);
+      SPB_PROBE1(7);
       mbar_wait(a2_empty(buf), ph ^ 1);
+      SPB_PROBE1(8);
       tc_fence_after();
       uint32_t v[2][32];
       const uint32_t taddr = tmem_base + 128 + buf * 128 + chalf * 32 + ((uint32_t)(quad * 32) << 16);
@@ -858,62 +914,32 @@ __global__ void __launch_bounds__(448, 1) conv1_fused_kernel(const __grid_consta
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       mbar_arrive(a2_full(buf));
+      SPB_PROBE1(9);
     }
   } else {
-    // =========================== conv1b epilogue (warps 2..5): bias + ReLU + 2x2 max-pool + bf16 ===========
-    const int quad = warp & 3;
+    // =========================== conv1b epilogue (warps 2..9): bias + ReLU + 2x2 max-pool + bf16 ===========
+    const int quad = warp & 3, chalf = (warp - 2) >> 2;
     const int m = quad * 32 + lane, py = m >> 3, px = m & 7;
     int it = 0;
     for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x, ++it) {
       const int buf = it & 1, ph = (it >> 1) & 1;
       const int n = t / tiles_per_view, rem = t % tiles_per_view;
       const int y = (rem / a.tiles_x) * 16 + py, x = (rem % a.tiles_x) * 8 + px;
+      if (a.dbg && blockIdx.x == 0 && it < 64 && threadIdx.x == 64) a.dbg[it * 16 + 10] = clock64();
       mbar_wait(acc2_full(buf), ph);
+      if (a.dbg && blockIdx.x == 0 && it < 64 && threadIdx.x == 64) a.dbg[it * 16 + 11] = clock64();
       tc_fence_after();
-      const uint32_t taddr = tmem_base + buf * 64 + ((uint32_t)(quad * 32) << 16);
+      const uint32_t taddr = tmem_base + buf * 64 + chalf * 32 + ((uint32_t)(quad * 32) << 16);
       const bool valid = y < a.H && x < a.W && !(px & 1) && !(py & 1);
       const long long opix = ((long long)n * (a.H >> 1) + (y >> 1)) * (a.W >> 1) + (x >> 1);
-      uint32_t v[2][32];
-      tc_ld_nowait<32>(taddr, v[0]);
-#pragma unroll
-      for (int b = 0; b < 2; ++b) {
-        tc_wait_ld();
-        if (b == 0) {
-          tc_ld_nowait<32>(taddr + 32, v[1]);
-        } else {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(acc2_empty(buf));
-        }
-        float f[32];
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 bb = *reinterpret_cast<const float4*>(sm.bias2 + b * 32 + j);
-          f[j] = __uint_as_float(v[b][j]) + bb.x;
-          f[j + 1] = __uint_as_float(v[b][j + 1]) + bb.y;
-          f[j + 2] = __uint_as_float(v[b][j + 2]) + bb.z;
-          f[j + 3] = __uint_as_float(v[b][j + 3]) + bb.w;
-        }
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          f[j] = fmaxf(f[j], 0.f);
-          f[j] = fmaxf(f[j], __shfl_xor_sync(0xffffffffu, f[j], 1));
-          f[j] = fmaxf(f[j], __shfl_xor_sync(0xffffffffu, f[j], 8));
-        }
-        if (valid) {
-          __nv_bfloat16* o = a.out + opix * 64 + b * 32;
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            uint32_t pk[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const __nv_bfloat162 hh = __floats2bfloat162_rn(f[j + 2 * q], f[j + 2 * q + 1]);
-              pk[q] = *reinterpret_cast<const uint32_t*>(&hh);
-            }
-            *reinterpret_cast<uint4*>(o + j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          }
-        }
-      }
+      uint32_t v[32];
+      tc_ld_nowait<32>(taddr, v);
+      tc_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc2_empty(buf));
+      epi_bf16_32<true>(v, sm.bias2 + chalf * 32, valid, a.out + opix * 64 + chalf * 32);
+      if (a.dbg && blockIdx.x == 0 && it < 64 && threadIdx.x == 64) a.dbg[it * 16 + 12] = clock64();
     }
   }
   tc_fence_before();
@@ -1014,6 +1040,11 @@ int conv1a_tc(const LayerDev& L, const float* x, __nv_bfloat16* out, int B, int 
   return SPB_OK;
 }
 
+static long long* g_conv1_dbg = nullptr;
+extern "C" int spb_conv1_fused_set_probe(long long* dev_buf) {  // debug: timeline probe buffer [64][16] or NULL
+  g_conv1_dbg = dev_buf;
+  return SPB_OK;
+}
 static int g_fuse1 = 1;  // conv1a fused into conv1b's kernel (0: two kernels, for A/B tests)
 extern "C" int spb_conv_tc_set_fuse1(int on) {
   g_fuse1 = on ? 1 : 0;
@@ -1041,10 +1072,11 @@ int conv1_fused(const LayerDev& L1a, const LayerDev& L1b, const float* x, __nv_b
   a.tiles_x = ceil_div(W, 8);
   a.tiles_y = ceil_div(H, 16);
   a.ntiles = V * a.tiles_x * a.tiles_y;
+  a.dbg = g_conv1_dbg;
   const int smem = (int)sizeof(Conv1FusedSmem) + 1024;
   SPB_CHECK_CUDA(cudaFuncSetAttribute(conv1_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int grid = a.ntiles < kNumSMs ? a.ntiles : kNumSMs;
-  conv1_fused_kernel<<<grid, 448, smem, st>>>(tm_w2, a);
+  conv1_fused_kernel<<<grid, 576, smem, st>>>(tm_w2, a);
   SPB_CHECK_LAUNCH();
   return SPB_OK;
 }
@@ -1090,7 +1122,7 @@ static int launch(const LayerDev& L, const __nv_bfloat16* in, void* out, int B, 
   a.ntiles = B * a.tiles_x * a.tiles_y;
   SPB_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
   const int grid = a.ntiles < kNumSMs ? a.ntiles : kNumSMs;
-  conv_tc_kernel<C><<<grid, 192, C::SMEM, st>>>(tm_act, tm_wgt, a);
+  conv_tc_kernel<C><<<grid, C::THREADS, C::SMEM, st>>>(tm_act, tm_wgt, a);
   SPB_CHECK_LAUNCH();
   return SPB_OK;
 }

@@ -1,0 +1,28 @@
+"""Timeline probe of conv1_fused_kernel (CTA 0): per-iteration clock64 stamps of the MMA, stage-1 and epilogue roles."""
+import os, sys
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from pytorch_superpoint_b200 import SuperPointNet_b200, _lib
+from pytorch_superpoint_b200.synthetic import synthetic_state_dict
+L = _lib.lib()
+net = SuperPointNet_b200(); net.load_state_dict(synthetic_state_dict("gauss2", 1))
+x = torch.rand(100, 1, 240, 320, device="cuda")
+net.forward_nhwc(x, want_desc=False); torch.cuda.synchronize()
+buf = torch.zeros(64 * 16, dtype=torch.int64, device="cuda")
+L.spb_conv1_fused_set_probe(buf.data_ptr())
+net.forward_nhwc(x, want_desc=False); torch.cuda.synchronize()
+L.spb_conv1_fused_set_probe(None)
+d = buf.cpu().view(64, 16)
+t0 = int(d[8, 0])
+names = ["mma:iter", "mma:conv1a_issued", "mma:acc2_empty", "mma:a2_full", "mma:conv1b_issued", "s1:iter", "s1:built",
+         "s1:acc1_full", "s1:a2_empty", "s1:done", "e2:iter", "e2:acc2_full", "e2:done"]
+for it in range(8, 16):
+    print(f"it {it}: " + "  ".join(f"{names[k].split(':')[0][0:2]}{k}={int(d[it, k]) - t0}" for k in range(13)))
+import statistics
+per = [int(d[i + 1, 5] - d[i, 5]) for i in range(10, 60)]
+print("S1 period median", statistics.median(per))
+for a, b, nm in [(5, 6, "s1 build"), (6, 7, "s1 wait acc1_full"), (7, 8, "s1 wait a2_empty"), (8, 9, "s1 epi1"),
+                 (0, 1, "mma wait+issue conv1a"), (1, 2, "mma wait acc2_empty"), (2, 3, "mma wait a2_full"),
+                 (3, 4, "mma issue conv1b"), (10, 11, "e2 wait acc2_full"), (11, 12, "e2 work")]:
+    v = [int(d[i, b] - d[i, a]) for i in range(10, 60)]
+    print(f"{nm:26s} median {statistics.median(v):8.0f}  max {max(v)}")
