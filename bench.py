@@ -155,6 +155,7 @@ def run_b200(args):
     from pytorch_superpoint_b200.export import HAExporter
     from pytorch_superpoint_b200.homographies import make_ha_homographies
 
+    os.environ.pop("NCCL_DEBUG", None)  # keep stdout to the single JSON line (NCCL prints its version banner there)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -322,10 +323,10 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=12)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--images", type=int, default=8, help="images per step")
+    ap.add_argument("--images", type=int, default=32, help="images per step (one batch)")
     ap.add_argument("--chunk", type=int, default=0, help="views per network pass (0 = all of the rank's views)")
     ap.add_argument("--ref-views", type=int, default=20, help="--impl reference: homographies per step (bounded sample)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
