@@ -171,7 +171,7 @@ struct ConvCfg {
   static constexpr bool POOL = POOL_;
   static constexpr int BW = (NPAD_ % 32 == 0) ? 32 : 16;  // TMEM columns per epilogue batch
   static constexpr int EPI_WARPS = OUT_ == 0 ? 8 : 4;     // bf16 layers: two warps per TMEM lane quadrant, half the columns each
-  static constexpr int THREADS = 64 + 32 * EPI_WARPS;
+  static constexpr int THREADS = 64 + 32 * EPI_WARPS + 32;  // + the second MMA issuer (last warp)
   static constexpr int STAGE_BYTES = OUT_ == 1 ? 4 * 32 * 65 * 4 : 0;
   static constexpr bool HALO = HALO_ && KS_ > 1, BRES = BRES_;
   static constexpr int TAPS = KS * KS, CHUNKS = CIN / 64;
@@ -185,7 +185,7 @@ struct ConvCfg {
   static constexpr int NBS = BRES ? NBLK : NB_;
   static constexpr int ACC_STRIDE = NPAD <= 64 ? 64 : (NPAD <= 128 ? 128 : 256);
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
-  static constexpr int NBAR = 2 * NA + 2 * NBS + 4;
+  static constexpr int NBAR = 2 * NA + 2 * NBS + 4 + 2;  // + the two issue tokens
   static constexpr size_t SMEM = 1024 /*align slack*/ + (size_t)NA * A_STRIDE + (size_t)NBS * B_BYTES + NPAD * 4 +
                                  NBAR * 8 + 16 + STAGE_BYTES;
   static_assert(B_BYTES % 1024 == 0, "weight block must keep 1024-byte alignment");
@@ -200,7 +200,7 @@ struct ConvArgs {
 };
 
 template <class C>
-__global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act,
+__global__ void __launch_bounds__(C::THREADS, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act,
                                                          const __grid_constant__ CUtensorMap tm_wgt, ConvArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space
@@ -217,6 +217,7 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
   auto b_empty = [&](int s) { return bar0 + 8u * (2 * C::NA + C::NBS + s); };
   auto acc_full = [&](int s) { return bar0 + 8u * (2 * C::NA + 2 * C::NBS + s); };
   auto acc_empty = [&](int s) { return bar0 + 8u * (2 * C::NA + 2 * C::NBS + 2 + s); };
+  auto token = [&](int s) { return bar0 + 8u * (2 * C::NA + 2 * C::NBS + 4 + s); };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -233,6 +234,7 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
     for (int s = 0; s < 2; ++s) {
       mbar_init(acc_full(s), 1);
       mbar_init(acc_empty(s), C::EPI_WARPS);
+      mbar_init(token(s), 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -289,21 +291,43 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
         first = false;
       }
     }
-  } else if (warp == 1) {
-    // =========================== MMA issuer ===========================
-    // The whole warp walks the pipeline converged (barrier waits by every lane); one elected lane issues
-    // tcgen05.mma / tcgen05.commit.  Descriptors are a per-stage 64-bit base plus compile-time constants
-    // (tap shift, 32-byte K step), so the per-MMA issue cost is a couple of integer adds.
+  } else if (warp == 1 || warp == 2 + C::EPI_WARPS) {
+    // =========================== MMA issuers ===========================
+    // TWO issuer warps alternate tiles (issuer q owns the tiles of parity q and the TMEM accumulator q).  The tensor
+    // pipe's queue is only a few MMAs deep, so with a single issuer the barrier waits between two tiles (a few
+    // hundred cycles of dependent shared-memory round trips) left the pipe idle ~1/3 of the time at N = 64.
+    // Now issuer q^1 finishes all waits for its tile while q is still issuing, then blocks on a token that q hands
+    // over BEFORE its last two tap groups: the other tile's MMAs queue up behind them and the pipe never drains.
+    // (Order between the two issuers' MMAs is irrelevant: different accumulators; every tcgen05.commit tracks the
+    // MMAs of its own thread only.)  Inside an issuer the whole warp walks the pipeline converged and one elected
+    // lane issues; descriptors are a per-stage base plus compile-time constants.
+    const int q = warp == 1 ? 0 : 1;
     constexpr uint32_t idesc = make_idesc(128, C::NPAD);
     constexpr uint64_t desc_hi_a = ((uint64_t)((C::P * 128) >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
     constexpr uint64_t desc_hi_b = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+    constexpr int A_PER_TILE = C::HALO ? C::CHUNKS : C::CHUNKS * C::TAPS;
+    // the token is handed over after this (chunk, tap) group has been issued
+    constexpr int PASS_KC = C::TAPS >= 3 ? C::CHUNKS - 1 : C::CHUNKS - 2;
+    constexpr int PASS_TAP = C::TAPS >= 3 ? C::TAPS - 3 : 0;
+    static_assert(PASS_KC >= 0, "token hand-over point");
+    auto advance = [](int& s, int& p, int n, int ring) {
+      s += n;
+      while (s >= ring) { s -= ring; p ^= 1; }
+    };
     const uint32_t sA_u32 = smem_u32(sA), sB_u32 = smem_u32(sB);
-    int sa = 0, pa = 0, sb = 0, pb = 0, as = 0, pacc = 0;
-    bool first = true;
-    for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x) {
-      mbar_wait(acc_empty(as), pacc ^ 1);
+    int sa = 0, pa = 0, sb = 0, pb = 0;
+    if (q == 1) {
+      advance(sa, pa, A_PER_TILE, C::NA);
+      if (!C::BRES) advance(sb, pb, C::NBLK, C::NBS);
+    }
+    const uint32_t d_tmem = tmem_base + (uint32_t)q * C::ACC_STRIDE;
+    int k = 0;  // this issuer's tile counter
+    for (int t = blockIdx.x + q * gridDim.x; t < a.ntiles; t += 2 * gridDim.x, ++k) {
+      const bool first = k == 0;
+      mbar_wait(acc_empty(q), (k & 1) ^ 1);
+      mbar_wait(a_full(sa), pa);  // first operand block of the tile (waited again, for free, in the loop)
+      if (q == 1 || k > 0) mbar_wait(token(q), (q == 0 ? k - 1 : k) & 1);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)as * C::ACC_STRIDE;
 #pragma unroll 1
       for (int kc = 0; kc < C::CHUNKS; ++kc) {
         if (C::HALO) mbar_wait(a_full(sa), pa);
@@ -322,13 +346,14 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
           const uint64_t bdesc = desc_hi_b | (uint64_t)(((sB_u32 + (uint32_t)slot * C::B_BYTES) >> 4) | (1u << 16));
           if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              tc_mma(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
-                     (kc | tap | k) != 0 ? 1u : 0u);
+            for (int kk = 0; kk < 4; ++kk)
+              tc_mma(d_tmem, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc,
+                     (kc | tap | kk) != 0 ? 1u : 0u);
             if (!C::BRES) tc_commit(b_empty(sb));
             if (!C::HALO) tc_commit(a_empty(sa));
             if (C::HALO && tap == C::TAPS - 1) tc_commit(a_empty(sa));
-            if (kc == C::CHUNKS - 1 && tap == C::TAPS - 1) tc_commit(acc_full(as));
+            if (kc == C::CHUNKS - 1 && tap == C::TAPS - 1) tc_commit(acc_full(q));
+            if (kc == PASS_KC && tap == PASS_TAP) mbar_arrive(token(q ^ 1));
           }
           __syncwarp();
           if (!C::BRES) {
@@ -342,8 +367,9 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
           if (++sa == C::NA) { sa = 0; pa ^= 1; }
         }
       }
-      first = false;
-      if (++as == 2) { as = 0; pacc ^= 1; }
+      // skip the other issuer's tile in both rings
+      advance(sa, pa, A_PER_TILE, C::NA);
+      if (!C::BRES) advance(sb, pb, C::NBLK, C::NBS);
     }
   } else {
     // =========================== epilogue (warps 2..5, or 2..9 for the bf16 layers) ===========================
@@ -705,13 +731,18 @@ struct Conv1FusedSmem {
   uint8_t a1[2][8192];      // conv1a im2col: 256 rows x 32 B, no-swizzle core matrices
   uint8_t b1[2048];         // conv1a weights [64][16]
   float patch[2][20 * 12];  // zero-padded 20x12 fp32 image patch under the halo block (rows y0-2.., cols x0-2..)
+  unsigned mrow[2][16];     // valid-mask bits of the tile's 16 rows x 8 pixels (homography-warp mode)
   float bias1[64], bias2[64];
-  uint64_t bars[9 + 14];    // b_full[9], a1_full[2], acc1_full[2], acc1_empty[2], a2_full[2], a2_empty[2], acc2_full[2], acc2_empty[2]
+  uint64_t bars[9 + 14 + 2];  // b_full[9], a1_full[2], acc1_full[2], acc1_empty[2], a2_full[2], a2_empty[2], acc2_full[2], acc2_empty[2], token[2]
   uint32_t tmem_slot;
 };
 
 struct Conv1FusedArgs {
-  const float* x;               // [V,H,W] fp32 views
+  const float* x;               // [V,H,W] fp32 views -- or, in warp mode (mats != NULL), the SOURCE images [V/vpi,H,W]
+  const float* mats;            // warp mode: forward homographies (view n uses mats[n] or mats[n % vpi] when shared)
+  uint8_t* bits;                // warp mode: valid-mask bits out, [V,H,W/8]
+  int vpi, shared_mats;
+  Lin lx, ly;
   const __nv_bfloat16* w1a;     // [64][16]
   const float *bias1, *bias2;
   __nv_bfloat16* out;           // [V,H/2,W/2,64]
@@ -732,7 +763,9 @@ __global__ void __launch_bounds__(576, 1) conv1_fused_kernel(const __grid_consta
   auto a2_empty = [&](int s) { return bar0 + 8u * (17 + s); };
   auto acc2_full = [&](int s) { return bar0 + 8u * (19 + s); };
   auto acc2_empty = [&](int s) { return bar0 + 8u * (21 + s); };
+  auto token = [&](int s) { return bar0 + 8u * (23 + s); };
 
+  if (threadIdx.x < 32) sm.mrow[threadIdx.x >> 4][threadIdx.x & 15] = 0u;
   if (threadIdx.x < 64) {
     sm.bias1[threadIdx.x] = a.bias1[threadIdx.x];
     sm.bias2[threadIdx.x] = a.bias2[threadIdx.x];
@@ -751,6 +784,7 @@ __global__ void __launch_bounds__(576, 1) conv1_fused_kernel(const __grid_consta
       mbar_init(a2_empty(s), 1);
       mbar_init(acc2_full(s), 1);
       mbar_init(acc2_empty(s), 8);
+      mbar_init(token(s), 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -768,65 +802,72 @@ __global__ void __launch_bounds__(576, 1) conv1_fused_kernel(const __grid_consta
   // TMEM columns: conv1b accumulators [0,64) [64,128); conv1a accumulators buffer j at 128 + 128 j (two M halves)
   const int tiles_per_view = a.tiles_x * a.tiles_y;
 
-  if (warp == 0) {
-    if (lane == 0) {
+  if (warp <= 1) {
+    // =========================== MMA issuers (warp 0 also loads the conv1b weights first) ===========================
+    // Issuer q owns the tiles of parity q: conv1a(j) into acc1[q], conv1b(j) into acc2[q].  The two issuers take
+    // turns on conv1b through a token handed over before the last two taps (see conv_tc_kernel), so one of them is
+    // always through its barrier waits when the other runs out of MMAs.  Global MMA order stays
+    // ... conv1b(j) | conv1a(j+2) | conv1b(j+1) | conv1a(j+3) ...  : stage 1 works one tile ahead of conv1b.
+    const int q = warp;
+    if (q == 0 && lane == 0) {
       for (int tap = 0; tap < 9; ++tap) {
         mbar_expect_tx(b_full(tap), 8192);
         tma_load_2d(smem_u32(sm.b2[tap]), &tm_w2, b_full(tap), tap * 64, 0);
       }
     }
-  } else if (warp == 1) {
-    // =========================== MMA issuer ===========================
+    __syncwarp();
     constexpr uint32_t idesc = make_idesc(128, 64);
     constexpr uint64_t hi_a2 = ((uint64_t)(1280 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
     constexpr uint64_t hi_b2 = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
     const uint64_t b1desc = make_desc_noswz(smem_u32(sm.b1), 128, 256);
-    auto issue_conv1a = [&](int it) {
-      const int buf = it & 1, ph = (it >> 1) & 1;
-      mbar_wait(acc1_empty(buf), ph ^ 1);
-      mbar_wait(a1_full(buf), ph);
+    const uint64_t a1desc = make_desc_noswz(smem_u32(sm.a1[q]), 128, 256);
+    const uint32_t acc1 = tmem_base + 128 + q * 128, acc2 = tmem_base + q * 64;
+    const uint32_t a2 = smem_u32(sm.a2[q]);
+    auto issue_conv1a = [&](int k) {  // this issuer's k-th tile
+      mbar_wait(acc1_empty(q), (k & 1) ^ 1);
+      mbar_wait(a1_full(q), k & 1);
       tc_fence_after();
       if (elect_one()) {
-        const uint32_t a1 = smem_u32(sm.a1[buf]);
-        tc_mma(tmem_base + 128 + buf * 128, make_desc_noswz(a1, 128, 256), b1desc, idesc, 0u);
-        tc_mma(tmem_base + 128 + buf * 128 + 64, make_desc_noswz(a1 + 4096, 128, 256), b1desc, idesc, 0u);
-        tc_commit(acc1_full(buf));
+        tc_mma(acc1, a1desc, b1desc, idesc, 0u);
+        tc_mma(acc1 + 64, a1desc + (uint64_t)(4096 >> 4), b1desc, idesc, 0u);
+        tc_commit(acc1_full(q));
       }
       __syncwarp();
     };
-    int it = 0;
 #define SPB_PROBE(slot)                                                                       \
   if (a.dbg && blockIdx.x == 0 && it < 64 && lane == 0) a.dbg[it * 16 + (slot)] = clock64()
-    if ((int)blockIdx.x < a.ntiles) issue_conv1a(0);
-    for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x, ++it) {
+    int k = 0;
+    if ((int)(blockIdx.x + q * gridDim.x) < a.ntiles) issue_conv1a(0);
+    for (int t = blockIdx.x + q * gridDim.x; t < a.ntiles; t += 2 * gridDim.x, ++k) {
+      const int it = 2 * k + q;
       SPB_PROBE(0);
-      if (t + (int)gridDim.x < a.ntiles) issue_conv1a(it + 1);
+      mbar_wait(acc2_empty(q), (k & 1) ^ 1);
       SPB_PROBE(1);
-      const int buf = it & 1, ph = (it >> 1) & 1;
-      mbar_wait(acc2_empty(buf), ph ^ 1);
+      mbar_wait(a2_full(q), k & 1);
       SPB_PROBE(2);
-      mbar_wait(a2_full(buf), ph);
+      if (q == 1 || k > 0) mbar_wait(token(q), (q == 0 ? k - 1 : k) & 1);
       SPB_PROBE(3);
       tc_fence_after();
-      const uint32_t a2 = smem_u32(sm.a2[buf]);
 #pragma unroll
       for (int tap = 0; tap < 9; ++tap) {
-        if (it == 0) mbar_wait(b_full(tap), 0);
+        if (k == 0) mbar_wait(b_full(tap), 0);
         const uint32_t tap_off = ((tap / 3) * 10 + (tap % 3)) * 128;
         const uint64_t adesc = hi_a2 | (uint64_t)(((a2 + tap_off) >> 4) | (1u << 16));
         const uint64_t bdesc = hi_b2 | (uint64_t)((smem_u32(sm.b2[tap]) >> 4) | (1u << 16));
         if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            tc_mma(tmem_base + buf * 64, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (tap | k) != 0 ? 1u : 0u);
+          for (int kk = 0; kk < 4; ++kk)
+            tc_mma(acc2, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, (tap | kk) != 0 ? 1u : 0u);
+          if (tap == 6) mbar_arrive(token(q ^ 1));
           if (tap == 8) {
-            tc_commit(a2_empty(buf));
-            tc_commit(acc2_full(buf));
+            tc_commit(a2_empty(q));
+            tc_commit(acc2_full(q));
           }
         }
         __syncwarp();
       }
       SPB_PROBE(4);
+      if (t + 2 * (int)gridDim.x < a.ntiles) issue_conv1a(k + 1);
     }
   } else if (warp >= 10) {
     // =========================== stage 1: im2col build + conv1a epilogue into conv1b's A operand =========
@@ -834,16 +875,50 @@ __global__ void __launch_bounds__(576, 1) conv1_fused_kernel(const __grid_consta
     const int quad = warp & 3;                   // TMEM lane quadrant of this warp
     const int chalf = (warp - 10) >> 2;          // which 32 of the 64 conv1a channels this warp converts
     const int lrow = quad * 32 + lane;           // TMEM lane; the thread owns halo pixels lrow and lrow + 128
-    auto patch_load = [&](int t) -> float {      // element sid of the 20x12 patch of tile t (zero outside the image)
-      if (sid >= 240) return 0.f;
+    // Element sid of the 20x12 patch of tile t (zero outside the image).  In warp mode the pixel of view n is
+    // produced here from the source image -- the homography warp (utils/utils.py:318-351, datasets/Coco.py:279)
+    // is fused into conv1's producer and the warped view never exists in memory; the sign bit of the returned
+    // word carries the nearest-mode validity of the same coordinates (utils/utils.py:696) for the mask bits.
+    struct PatchVal {
+      float v;
+      unsigned valid;
+    };
+    auto patch_load = [&](int t) -> PatchVal {
+      PatchVal r{0.f, 0u};
+      if (sid >= 240) return r;
       const int n = t / tiles_per_view, rem = t % tiles_per_view;
       const int yy = (rem / a.tiles_x) * 16 - 2 + sid / 12, xx = (rem % a.tiles_x) * 8 - 2 + sid % 12;
-      return (yy >= 0 && yy < a.H && xx >= 0 && xx < a.W) ? __ldg(a.x + ((long long)n * a.H + yy) * a.W + xx) : 0.f;
+      if (!(yy >= 0 && yy < a.H && xx >= 0 && xx < a.W)) return r;
+      if (a.mats == nullptr) {
+        r.v = __ldg(a.x + ((long long)n * a.H + yy) * a.W + xx);
+        return r;
+      }
+      const Mat3 M = load_mat(a.mats + 9 * (a.shared_mats ? n % a.vpi : n));
+      const float* src = a.x + (long long)(n / a.vpi) * a.H * a.W;
+      float ix, iy;
+      warp_coord(M, a.lx.at(xx), a.ly.at(yy), a.W, a.H, ix, iy);
+      const Taps tp = make_taps(ix, iy);
+      r.v = bilinear(tp, a.W, a.H, [&](int sx, int sy) { return __ldg(src + (long long)sy * a.W + sx); });
+      r.valid = in_bounds(rintf(ix), rintf(iy), a.W, a.H) ? 1u : 0u;
+      return r;
     };
-    auto build = [&](float pv, int t, int buf) {  // patch -> K=16 im2col rows of the 180 halo pixels of tile t
+    auto build = [&](PatchVal pv, int t, int buf, int pit) {  // patch -> K=16 im2col rows of the 180 halo pixels of tile t
+      auto probe = [&](int slot) {
+        if (a.dbg && blockIdx.x == 0 && pit >= 0 && pit < 64 && threadIdx.x == 320) a.dbg[pit * 16 + slot] = clock64();
+      };
       const int y0 = ((t % tiles_per_view) / a.tiles_x) * 16, x0 = ((t % tiles_per_view) % a.tiles_x) * 8;
-      if (sid < 240) sm.patch[buf][sid] = pv;
+      if (sid < 240) {
+        sm.patch[buf][sid] = pv.v;
+        const int pr = sid / 12 - 2, pc = sid % 12 - 2;  // position inside the 16x8 tile
+        if (a.bits && pv.valid && pr >= 0 && pr < 16 && pc >= 0 && pc < 8) atomicOr(&sm.mrow[buf][pr], 1u << pc);
+      }
       named_bar_sync(2, 256);
+      probe(13);
+      if (a.bits && sid < 16) {
+        if (y0 + sid < a.H && x0 < a.W)
+          a.bits[((long long)(t / tiles_per_view) * a.H + y0 + sid) * (a.W >> 3) + (x0 >> 3)] = (uint8_t)sm.mrow[buf][sid];
+        sm.mrow[buf][sid] = 0u;
+      }
       if (sid < 180) {
         const float* pp = sm.patch[buf] + (sid / 10) * 12 + sid % 10;  // tap (0,0) of halo pixel sid
         // conv1b zero-pads conv1a's OUTPUT: a halo pixel outside the image must come out as exactly 0, so its
@@ -865,13 +940,15 @@ __global__ void __launch_bounds__(576, 1) conv1_fused_kernel(const __grid_consta
         *reinterpret_cast<uint4*>(row) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         *reinterpret_cast<uint4*>(row + 128) = make_uint4(pk[4], inside ? 0x00003F80u : 0u, 0, 0);  // slot 10: bias tail
       }
+      probe(14);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       mbar_arrive(a1_full(buf));
+      probe(15);
     };
     int it = 0;
-    float pv = 0.f;
+    PatchVal pv{0.f, 0u};
     if ((int)blockIdx.x < a.ntiles) {
-      build(patch_load(blockIdx.x), blockIdx.x, 0);
+      build(patch_load(blockIdx.x), blockIdx.x, 0, -1);
       if ((int)(blockIdx.x + gridDim.x) < a.ntiles) pv = patch_load(blockIdx.x + gridDim.x);
     }
     for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x, ++it) {
@@ -879,7 +956,7 @@ __global__ void __launch_bounds__(576, 1) conv1_fused_kernel(const __grid_consta
   if (a.dbg && blockIdx.x == 0 && it < 64 && threadIdx.x == 320) a.dbg[it * 16 + (slot)] = clock64()
       SPB_PROBE1(5);
       if (t + (int)gridDim.x < a.ntiles) {
-        build(pv, t + gridDim.x, (it + 1) & 1);                                    // im2col of tile it+1
+        build(pv, t + gridDim.x, (it + 1) & 1, it);                                // im2col of tile it+1
         if (t + 2 * (int)gridDim.x < a.ntiles) pv = patch_load(t + 2 * gridDim.x);  // prefetch for tile it+2
       }
       SPB_PROBE1(6);
@@ -1051,9 +1128,17 @@ extern "C" int spb_conv_tc_set_fuse1(int on) {
   return SPB_OK;
 }
 bool conv1_fused_enabled() { return g_fuse1 != 0; }
+// Homography warp + valid-mask bits produced inside conv1's stage 1 instead of by warp_bits_kernel.  Bit-identical
+// results, but the 4-tap gathers lengthen stage 1 (the critical producer of the fused block), so it is OFF by default.
+static int g_fuse_warp = 0;
+extern "C" int spb_conv_tc_set_fuse_warp(int on) {
+  g_fuse_warp = on ? 1 : 0;
+  return SPB_OK;
+}
+bool conv1_warp_fused_enabled() { return g_fuse1 != 0 && g_fuse_warp != 0; }
 
 int conv1_fused(const LayerDev& L1a, const LayerDev& L1b, const float* x, __nv_bfloat16* out, int V, int H, int W,
-                cudaStream_t st) {
+                const ViewSource* vs, cudaStream_t st) {
   if ((H | W) & 1) {
     set_error("conv1_fused: pooled block needs even H, W (got %dx%d)", H, W);
     return SPB_EINVAL;
@@ -1062,6 +1147,16 @@ int conv1_fused(const LayerDev& L1a, const LayerDev& L1b, const float* x, __nv_b
   memcpy(&tm_w2, L1b.tmap_w, sizeof(tm_w2));
   Conv1FusedArgs a;
   a.x = x;
+  a.mats = vs ? vs->mats : nullptr;
+  a.bits = vs ? vs->bits : nullptr;
+  a.vpi = vs ? vs->vpi : 1;
+  a.shared_mats = vs ? vs->shared_mats : 0;
+  a.lx = Lin(W);
+  a.ly = Lin(H);
+  if (vs && (W & 7)) {
+    set_error("conv1_fused: warp mode needs W %% 8 == 0 (got %d)", W);
+    return SPB_EINVAL;
+  }
   a.w1a = L1a.w_tc;
   a.bias1 = L1a.bias;
   a.bias2 = L1b.bias;

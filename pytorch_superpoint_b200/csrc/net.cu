@@ -99,8 +99,9 @@ static int run_layer(const Net* net, int li, const void* in, void* out, int B, i
 }
 
 // semi: logits [B,Hc,Wc,65] (or NULL); probs: softmax probabilities [B,Hc,Wc,64] (or NULL); desc optional
+// vs != NULL (tcgen05 + fused first block only): x holds SOURCE images and the homography warp happens inside conv1
 static int forward(const Net* net, const float* x, int B, int H, int W, float* semi, float* probs, float* desc,
-                   void* ws, cudaStream_t st) {
+                   void* ws, cudaStream_t st, const ViewSource* vs = nullptr) {
   Workspace w(ws, B, H, W);
   int rc;
 #define RUN(li, in, out, h, wd, mode)                                     \
@@ -108,8 +109,12 @@ static int forward(const Net* net, const float* x, int B, int H, int W, float* s
   if (net->impl == SPB_IMPL_TCGEN05 && conv1_fused_enabled()) {
     // conv1a + conv1b + pool in one kernel: the 64-channel full-resolution activation never leaves the SM
     StageTimer tm(net, 1, st);
-    if ((rc = conv1_fused(net->layer[0], net->layer[1], x, w.buf1, B, H, W, st)) != SPB_OK) return rc;
+    if ((rc = conv1_fused(net->layer[0], net->layer[1], x, w.buf1, B, H, W, vs, st)) != SPB_OK) return rc;
   } else {
+    if (vs) {
+      set_error("forward: warp-fused input needs the tcgen05 fused first block");
+      return SPB_EINVAL;
+    }
     RUN(0, x, w.buf0, H, W, 0);
     RUN(1, w.buf0, w.buf1, H, W, 0);  // + pool -> H/2
   }
@@ -343,16 +348,23 @@ int spb_ha_heatmap_sums_batch(spb_net* h, const float* imgs, const float* mats_u
       const long long moff = shared_mats ? 9LL * n0 : 9LL * ((long long)b0 * N + n0);
       // per-image matrix sets are only contiguous over a whole image: view chunks imply bg == 1
       int rc;
-      {
-        StageTimer tm(net, 12, st);
-        rc = warp_with_mask_bits(imgs + (long long)b0 * H * W, mats_fwd + moff, warped, bits, bg * nn, nn, shared_mats,
-                                 H, W, st);
+      if (tc && conv1_warp_fused_enabled()) {
+        // warp + valid mask are fused into the first conv block: source images go straight into the network
+        ViewSource vs = {mats_fwd + moff, bits, nn, shared_mats};
+        rc = forward(net, imgs + (long long)b0 * H * W, bg * nn, H, W, nullptr, probs, nullptr, base + L.net, st, &vs);
+        if (rc != SPB_OK) return rc;
+      } else {
+        {
+          StageTimer tm(net, 12, st);
+          rc = warp_with_mask_bits(imgs + (long long)b0 * H * W, mats_fwd + moff, warped, bits, bg * nn, nn,
+                                   shared_mats, H, W, st);
+        }
+        if (rc != SPB_OK) return rc;
+        // the detector head writes softmax probabilities directly (tcgen05 epilogue); the validation path goes
+        // through logits + a softmax kernel
+        rc = forward(net, warped, bg * nn, H, W, tc ? nullptr : semi, probs, nullptr, base + L.net, st);
+        if (rc != SPB_OK) return rc;
       }
-      if (rc != SPB_OK) return rc;
-      // the detector head writes softmax probabilities directly (tcgen05 epilogue); the validation path goes
-      // through logits + a softmax kernel
-      rc = forward(net, warped, bg * nn, H, W, tc ? nullptr : semi, probs, nullptr, base + L.net, st);
-      if (rc != SPB_OK) return rc;
       {
         StageTimer tm(net, 13, st);
         rc = aggregate_probs(probs, bits, mats_unwarp + moff, shared_mats, bg, nn, H, W,

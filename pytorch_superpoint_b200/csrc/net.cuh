@@ -46,9 +46,17 @@ int aggregate_probs(const float* probs, const uint8_t* bits, const float* mats_u
 
 // conv_tc.cu (tcgen05 / TMEM / TMA)
 int conv1a_tc(const LayerDev& L, const float* x, __nv_bfloat16* out, int B, int H, int W, cudaStream_t st);
+// Homography-warp mode of the fused first block: the kernel reads SOURCE images and warps on the fly.
+struct ViewSource {
+  const float* mats;  // forward homographies (sample['inv_homographies'])
+  uint8_t* bits;      // valid-mask bits out [V,H,W/8]
+  int vpi;            // views per source image
+  int shared_mats;    // matrices shared by all images (index n % vpi) or per image (index n)
+};
 bool conv1_fused_enabled();
+bool conv1_warp_fused_enabled();
 int conv1_fused(const LayerDev& L1a, const LayerDev& L1b, const float* x, __nv_bfloat16* out, int V, int H, int W,
-                cudaStream_t st);
+                const ViewSource* vs, cudaStream_t st);
 int conv_tc_prepare(LayerDev& L);  // builds the weight tensor map after w_tc is uploaded
 // out_mode: 0 bf16 NHWC, 1 fp32 rows (cout channels), 2 fp32 rows L2-normalised, 3 softmax probabilities
 // (convPb only: fp32 [.,64], dustbin dropped)

@@ -187,3 +187,28 @@ def test_conv1_fused_block_equals_two_kernels(net, B, H, W):
     assert torch.isfinite(s1).all()
     assert (s0 - s1).abs().max().item() <= 1e-5  # same bf16 intermediate, same accumulation order
     assert (d0 - d1).abs().max().item() <= 1e-6
+
+
+@pytest.mark.parametrize("H,W,N", [(48, 64, 6), (240, 320, 12), (40, 24, 3)])
+def test_ha_warp_fused_into_conv1_equals_separate_warp_kernel(H, W, N):
+    """HA path with the homography warp + valid-mask bits produced inside the fused first conv block
+    == HA path with the stand-alone warp kernel and the two-kernel first block."""
+    from pytorch_superpoint_b200 import SuperPointNet_b200, _lib, make_ha_homographies
+    L = _lib.lib()
+    n = SuperPointNet_b200()
+    n.load_state_dict(O.synthetic_state_dict("gauss2", seed=2))
+    B = 2
+    imgs = torch.rand(B, H, W, device="cuda", generator=torch.Generator("cuda").manual_seed(H + N))
+    mu, mf = make_ha_homographies(N, seed=H)
+    mu, mf = torch.from_numpy(mu).cuda(), torch.from_numpy(mf).cuda()
+    try:
+        L.spb_conv_tc_set_fuse1(0)
+        ref = n.ha_heatmap_sums_batch(imgs, mu, mf).clone()
+        L.spb_conv_tc_set_fuse1(1)
+        L.spb_conv_tc_set_fuse_warp(1)
+        out = n.ha_heatmap_sums_batch(imgs, mu, mf).clone()
+    finally:
+        L.spb_conv_tc_set_fuse1(1)
+        L.spb_conv_tc_set_fuse_warp(0)
+    assert torch.equal(out[:, 1], ref[:, 1])                       # sum of masks: identical bits
+    assert (out[:, 0] - ref[:, 0]).abs().max().item() <= 1e-6      # sum of heat*mask

@@ -14,15 +14,18 @@ net.forward_nhwc(x, want_desc=False); torch.cuda.synchronize()
 L.spb_conv1_fused_set_probe(None)
 d = buf.cpu().view(64, 16)
 t0 = int(d[8, 0])
-names = ["mma:iter", "mma:conv1a_issued", "mma:acc2_empty", "mma:a2_full", "mma:conv1b_issued", "s1:iter", "s1:built",
-         "s1:acc1_full", "s1:a2_empty", "s1:done", "e2:iter", "e2:acc2_full", "e2:done"]
-for it in range(8, 16):
-    print(f"it {it}: " + "  ".join(f"{names[k].split(':')[0][0:2]}{k}={int(d[it, k]) - t0}" for k in range(13)))
+names = ["mma:iter", "mma:acc2_empty", "mma:a2_full", "mma:token", "mma:conv1b_issued", "s1:iter", "s1:built",
+         "s1:acc1_full", "s1:a2_empty", "s1:done", "e2:iter", "e2:acc2_full", "e2:done", "s1:bar", "s1:sts", "s1:arrived"]
+for it in range(8, 14):
+    print(f"it {it}: " + "  ".join(f"{names[k].replace(':', '.')}={int(d[it, k]) - t0}" for k in range(16)))
 import statistics
 per = [int(d[i + 1, 5] - d[i, 5]) for i in range(10, 60)]
 print("S1 period median", statistics.median(per))
-for a, b, nm in [(5, 6, "s1 build"), (6, 7, "s1 wait acc1_full"), (7, 8, "s1 wait a2_empty"), (8, 9, "s1 epi1"),
-                 (0, 1, "mma wait+issue conv1a"), (1, 2, "mma wait acc2_empty"), (2, 3, "mma wait a2_full"),
+for a, b, nm in [(5, 13, "s1 patch store + named barrier"), (13, 14, "s1 im2col lds/sts"), (14, 15, "s1 fence+arrive"),
+                 (15, 6, "s1 prefetch issue"), (6, 7, "s1 wait acc1_full"), (7, 8, "s1 wait a2_empty"),
+                 (8, 9, "s1 epi1"), (0, 1, "mma wait acc2_empty"), (1, 2, "mma wait a2_full"), (2, 3, "mma wait token"),
                  (3, 4, "mma issue conv1b"), (10, 11, "e2 wait acc2_full"), (11, 12, "e2 work")]:
     v = [int(d[i, b] - d[i, a]) for i in range(10, 60)]
-    print(f"{nm:26s} median {statistics.median(v):8.0f}  max {max(v)}")
+    print(f"{nm:32s} median {statistics.median(v):8.0f}  max {max(v)}")
+v = [int(d[i + 2, 0] - d[i, 4]) for i in range(10, 58)]
+print(f"{'mma issuer: conv1b done -> next':32s} median {statistics.median(v):8.0f}  max {max(v)}")
