@@ -15,150 +15,9 @@
 //     epilogue warps read TMEM with tcgen05.ld and apply bias + ReLU + 2x2 max-pool (lane shuffles)
 //     + bf16 pack (or fp32 / channel-L2-normalised output for the two heads).
 // Warp roles: 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2..5 = epilogue.
-#include <cuda.h>
-
-#include "net.cuh"
+#include "tc_common.cuh"
 
 namespace spb {
-
-// ------------------------------------------------------------------------------------------------
-// PTX wrappers
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-// Bounded wait: a protocol bug must abort the kernel, not hang the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok = 0;
-  const long long t0 = clock64();
-  while (true) {
-    asm volatile(
-        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (ok) return;
-    if (clock64() - t0 > 4000000000LL) {
-      printf("spb200 conv_tc: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x,
-             threadIdx.x, bar, parity);
-      __trap();
-    }
-  }
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
-                                            int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
-  return pred != 0;
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-      : "memory");
-}
-__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-template <int BW>
-__device__ __forceinline__ void tc_ld_nowait(uint32_t taddr, uint32_t (&v)[BW]);
-template <>
-__device__ __forceinline__ void tc_ld_nowait<16>(uint32_t taddr, uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr));
-}
-template <>
-__device__ __forceinline__ void tc_ld_nowait<32>(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// 32 fp32 accumulator columns of one pixel -> + bias -> bf16x2 pack -> ReLU -> optional 2x2 max-pool with PACKED
-// lane shuffles (lane = 4 tile rows x 8 tile columns: partners are lane^1 and lane^8; max commutes with the
-// monotone bf16 rounding, so pooling after the pack is exact) -> one 64-byte store by the lane that owns the output.
-template <bool POOL>
-__device__ __forceinline__ void epi_bf16_32(const uint32_t (&v)[32], const float* __restrict__ bias, bool valid,
-                                            __nv_bfloat16* __restrict__ o) {
-  uint32_t pk[16];
-  const __nv_bfloat162 zero = __floats2bfloat162_rn(0.f, 0.f);
-#pragma unroll
-  for (int j = 0; j < 32; j += 4) {
-    const float4 bb = *reinterpret_cast<const float4*>(bias + j);
-    __nv_bfloat162 h0 = __hmax2(__floats2bfloat162_rn(__uint_as_float(v[j]) + bb.x, __uint_as_float(v[j + 1]) + bb.y), zero);
-    __nv_bfloat162 h1 = __hmax2(__floats2bfloat162_rn(__uint_as_float(v[j + 2]) + bb.z, __uint_as_float(v[j + 3]) + bb.w), zero);
-    uint32_t u0 = *reinterpret_cast<const uint32_t*>(&h0), u1 = *reinterpret_cast<const uint32_t*>(&h1);
-    if (POOL) {
-#pragma unroll
-      for (int sh = 1; sh <= 8; sh <<= 3) {
-        const uint32_t p0 = __shfl_xor_sync(0xffffffffu, u0, sh), p1 = __shfl_xor_sync(0xffffffffu, u1, sh);
-        h0 = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&u0), *reinterpret_cast<const __nv_bfloat162*>(&p0));
-        h1 = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&u1), *reinterpret_cast<const __nv_bfloat162*>(&p1));
-        u0 = *reinterpret_cast<const uint32_t*>(&h0);
-        u1 = *reinterpret_cast<const uint32_t*>(&h1);
-      }
-    }
-    pk[j / 2] = u0;
-    pk[j / 2 + 1] = u1;
-  }
-  if (valid) {
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-      *reinterpret_cast<uint4*>(o + q * 8) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-  }
-}
-
-// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
-// [0,14) start>>4, [16,30) LBO>>4 (unused for swizzled K-major), [32,46) SBO>>4, [46,48) version=1,
-// [61,64) layout (2 = SWIZZLE_128B).
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo_bytes) {
-  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)1 << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) |
-         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
-}
-// kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, M x N.
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
 
 // ------------------------------------------------------------------------------------------------
 // configuration
@@ -173,6 +32,11 @@ struct ConvCfg {
   static constexpr int EPI_WARPS = OUT_ == 0 ? 8 : 4;     // bf16 layers: two warps per TMEM lane quadrant, half the columns each
   static constexpr int THREADS = 64 + 32 * EPI_WARPS + 32;  // + the second MMA issuer (last warp)
   static constexpr int STAGE_BYTES = OUT_ == 1 ? 4 * 32 * 65 * 4 : 0;
+  // bf16 layers with >= 128 output channels stage each warp's 32 pixels x 64 channels (4 KB, SWIZZLE_128B) and
+  // write it with one TMA tensor store: per-lane 16-byte global stores at a 256/512-byte stride cost one L1
+  // wavefront per lane, in the shared-memory pipe the tensor core reads its operands through
+  static constexpr bool TMA_OUT = OUT_ == 0 && NPAD_ >= 128;
+  static constexpr int OSTAGE_BYTES = TMA_OUT ? 8 * 4096 : 0;
   static constexpr bool HALO = HALO_ && KS_ > 1, BRES = BRES_;
   static constexpr int TAPS = KS * KS, CHUNKS = CIN / 64;
   static constexpr int TH = 16, TW = 8;
@@ -186,8 +50,8 @@ struct ConvCfg {
   static constexpr int ACC_STRIDE = NPAD <= 64 ? 64 : (NPAD <= 128 ? 128 : 256);
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
   static constexpr int NBAR = 2 * NA + 2 * NBS + 4 + 2;  // + the two issue tokens
-  static constexpr size_t SMEM = 1024 /*align slack*/ + (size_t)NA * A_STRIDE + (size_t)NBS * B_BYTES + NPAD * 4 +
-                                 NBAR * 8 + 16 + STAGE_BYTES;
+  static constexpr size_t SMEM = 1024 /*align slack*/ + (size_t)NA * A_STRIDE + (size_t)NBS * B_BYTES + OSTAGE_BYTES +
+                                 NPAD * 4 + NBAR * 8 + 16 + STAGE_BYTES;
   static_assert(B_BYTES % 1024 == 0, "weight block must keep 1024-byte alignment");
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
@@ -201,12 +65,14 @@ struct ConvArgs {
 
 template <class C>
 __global__ void __launch_bounds__(C::THREADS, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act,
-                                                         const __grid_constant__ CUtensorMap tm_wgt, ConvArgs a) {
+                                                                const __grid_constant__ CUtensorMap tm_wgt,
+                                                                const __grid_constant__ CUtensorMap tm_out, ConvArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space
   uint8_t* sA = smem;
   uint8_t* sB = sA + (size_t)C::NA * C::A_STRIDE;
-  float* sBias = reinterpret_cast<float*>(sB + (size_t)C::NBS * C::B_BYTES);
+  uint8_t* sOut = sB + (size_t)C::NBS * C::B_BYTES;  // 1024-byte aligned (A_STRIDE and B_BYTES are multiples of 1 KB)
+  float* sBias = reinterpret_cast<float*>(sOut + C::OSTAGE_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + C::NPAD);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + C::NBAR);
   float* sStage = reinterpret_cast<float*>(tmem_slot + 4);  // OUT == 1 only
@@ -460,7 +326,36 @@ __global__ void __launch_bounds__(C::THREADS, 1) conv_tc_kernel(const __grid_con
           if (lane == 0) mbar_arrive(acc_empty(as));
         }
         const int c0 = col0 + b * BW;
-        if constexpr (C::OUT == 0) {
+        if constexpr (C::TMA_OUT) {
+          // two 32-channel batches fill one 128-byte row per pixel of this warp's staging tile; then ONE TMA store
+          uint8_t* stg = sOut + (warp - 2) * 4096;
+          const int p = C::POOL ? (lane >> 4) * 4 + ((lane & 7) >> 1) : lane;  // staging row of this lane's pixel
+          uint32_t pk[16];
+          epi_pack32<C::POOL>(v[b & 1], sBias + c0, pk);
+          if ((b & 1) == 0) {  // the previous store out of this tile must have finished reading it
+            if (lane == 0) tma_store_wait_read<0>();
+            __syncwarp();
+          }
+          if (!C::POOL || !(lane & 9)) {
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4)
+              *reinterpret_cast<uint4*>(stg + p * 128 + ((((b & 1) * 4 + q4) ^ (p & 7)) * 16)) =
+                  make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
+          }
+          if (b & 1) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+              const int yq = y0 + 4 * quad;
+              if (C::POOL)
+                tma_store_4d(&tm_out, smem_u32(stg), c0 - 32, x0 >> 1, yq >> 1, n);
+              else
+                tma_store_4d(&tm_out, smem_u32(stg), c0 - 32, x0, yq, n);
+              tma_store_commit();
+            }
+          }
+          continue;
+        } else if constexpr (C::OUT == 0) {
           epi_bf16_32<C::POOL>(v[b & 1], sBias + c0, valid, static_cast<__nv_bfloat16*>(a.out) + opix * a.cout + c0);
           continue;
         }
@@ -529,6 +424,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) conv_tc_kernel(const __grid_con
       }
       if (++as == 2) { as = 0; pacc ^= 1; }
     }
+    if (C::TMA_OUT && lane == 0) tma_store_wait_read<0>();
   }
 
   tc_fence_before();
@@ -547,32 +443,6 @@ __global__ void __launch_bounds__(C::THREADS, 1) conv_tc_kernel(const __grid_con
 // per tile, epilogue bias + ReLU + bf16 and a fully contiguous 16 KB NHWC store.  HBM-write bound.
 // Warps 0..3: im2col build of tile i+1, then epilogue of tile i (double-buffered A and TMEM); warp 4: MMA.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint64_t make_desc_noswz(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
-         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | ((uint64_t)1 << 46);
-}
-
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0),
-               "r"(c1)
-               : "memory");
-}
-__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void tma_store_wait_read() {
-  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
-}
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-
-// two fp32 accumulators -> ReLU -> packed bf16x2 (pack first, then one packed max)
-__device__ __forceinline__ uint32_t relu_pack_bf16(uint32_t a, uint32_t b) {
-  const __nv_bfloat162 h = __hmax2(__floats2bfloat162_rn(__uint_as_float(a), __uint_as_float(b)),
-                                   __floats2bfloat162_rn(0.f, 0.f));
-  return *reinterpret_cast<const uint32_t*>(&h);
-}
-
 struct Conv1aSmem {
   uint8_t stage[2][16384];  // output tiles, 128 rows x 128 B, SWIZZLE_128B (TMA store source)
   uint8_t a[2][4096];       // im2col tiles
@@ -728,21 +598,17 @@ __global__ void __launch_bounds__(160, 4) conv1a_tc_kernel(const __grid_constant
 struct Conv1FusedSmem {
   uint8_t b2[9][8192];      // conv1b weights, 9 taps x [64 rows x 128 B], SWIZZLE_128B (TMA)
   uint8_t a2[2][23552];     // conv1b A operand: 18x10 halo pixels x 128 B, SWIZZLE_128B, written by stage-1
+  uint8_t ostage[2][4][1024];  // pooled output of one TMEM quadrant: 2 x 4 pixels x 128 B, SWIZZLE_128B (TMA store source)
   uint8_t a1[2][8192];      // conv1a im2col: 256 rows x 32 B, no-swizzle core matrices
   uint8_t b1[2048];         // conv1a weights [64][16]
-  float patch[2][20 * 12];  // zero-padded 20x12 fp32 image patch under the halo block (rows y0-2.., cols x0-2..)
-  unsigned mrow[2][16];     // valid-mask bits of the tile's 16 rows x 8 pixels (homography-warp mode)
+  float patch[4][320];      // zero-padded 20x16 fp32 image patch under the halo block (rows y0-2.., cols x0-4..), TMA
+  int2 origin[4];           // (x0, y0) of the tile each patch belongs to
   float bias1[64], bias2[64];
-  uint64_t bars[9 + 14 + 2];  // b_full[9], a1_full[2], acc1_full[2], acc1_empty[2], a2_full[2], a2_empty[2], acc2_full[2], acc2_empty[2], token[2]
+  uint64_t bars[9 + 14 + 2 + 4];  // b_full[9], a1_full[2], acc1_full[2], acc1_empty[2], a2_full[2], a2_empty[2], acc2_full[2], acc2_empty[2], token[2], patch_full[4]
   uint32_t tmem_slot;
 };
 
 struct Conv1FusedArgs {
-  const float* x;               // [V,H,W] fp32 views -- or, in warp mode (mats != NULL), the SOURCE images [V/vpi,H,W]
-  const float* mats;            // warp mode: forward homographies (view n uses mats[n] or mats[n % vpi] when shared)
-  uint8_t* bits;                // warp mode: valid-mask bits out, [V,H,W/8]
-  int vpi, shared_mats;
-  Lin lx, ly;
   const __nv_bfloat16* w1a;     // [64][16]
   const float *bias1, *bias2;
   __nv_bfloat16* out;           // [V,H/2,W/2,64]
@@ -750,7 +616,9 @@ struct Conv1FusedArgs {
   long long* dbg;               // optional timeline probe (CTA 0): [64 iterations][16 slots] of clock64, or NULL
 };
 
-__global__ void __launch_bounds__(576, 1) conv1_fused_kernel(const __grid_constant__ CUtensorMap tm_w2, Conv1FusedArgs a) {
+__global__ void __launch_bounds__(576, 1) conv1_fused_kernel(const __grid_constant__ CUtensorMap tm_w2,
+                                                             const __grid_constant__ CUtensorMap tm_out,
+                                                             const __grid_constant__ CUtensorMap tm_x, Conv1FusedArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   Conv1FusedSmem& sm = *reinterpret_cast<Conv1FusedSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -764,8 +632,8 @@ __global__ void __launch_bounds__(576, 1) conv1_fused_kernel(const __grid_consta
   auto acc2_full = [&](int s) { return bar0 + 8u * (19 + s); };
   auto acc2_empty = [&](int s) { return bar0 + 8u * (21 + s); };
   auto token = [&](int s) { return bar0 + 8u * (23 + s); };
+  auto patch_full = [&](int s) { return bar0 + 8u * (25 + s); };
 
-  if (threadIdx.x < 32) sm.mrow[threadIdx.x >> 4][threadIdx.x & 15] = 0u;
   if (threadIdx.x < 64) {
     sm.bias1[threadIdx.x] = a.bias1[threadIdx.x];
     sm.bias2[threadIdx.x] = a.bias2[threadIdx.x];
@@ -786,6 +654,7 @@ __global__ void __launch_bounds__(576, 1) conv1_fused_kernel(const __grid_consta
       mbar_init(acc2_empty(s), 8);
       mbar_init(token(s), 1);
     }
+    for (int s = 0; s < 4; ++s) mbar_init(patch_full(s), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -875,64 +744,43 @@ __global__ void __launch_bounds__(576, 1) conv1_fused_kernel(const __grid_consta
     const int quad = warp & 3;                   // TMEM lane quadrant of this warp
     const int chalf = (warp - 10) >> 2;          // which 32 of the 64 conv1a channels this warp converts
     const int lrow = quad * 32 + lane;           // TMEM lane; the thread owns halo pixels lrow and lrow + 128
-    // Element sid of the 20x12 patch of tile t (zero outside the image).  In warp mode the pixel of view n is
-    // produced here from the source image -- the homography warp (utils/utils.py:318-351, datasets/Coco.py:279)
-    // is fused into conv1's producer and the warped view never exists in memory; the sign bit of the returned
-    // word carries the nearest-mode validity of the same coordinates (utils/utils.py:696) for the mask bits.
-    struct PatchVal {
-      float v;
-      unsigned valid;
-    };
-    auto patch_load = [&](int t) -> PatchVal {
-      PatchVal r{0.f, 0u};
-      if (sid >= 240) return r;
-      const int n = t / tiles_per_view, rem = t % tiles_per_view;
-      const int yy = (rem / a.tiles_x) * 16 - 2 + sid / 12, xx = (rem % a.tiles_x) * 8 - 2 + sid % 12;
-      if (!(yy >= 0 && yy < a.H && xx >= 0 && xx < a.W)) return r;
-      if (a.mats == nullptr) {
-        r.v = __ldg(a.x + ((long long)n * a.H + yy) * a.W + xx);
-        return r;
+    // The zero-padded fp32 patch under tile j's halo block arrives by TMA (box 16 x 20 of the [V,H,W] view tensor
+    // at (x0-4, y0-2): the innermost start must be 16-byte aligned, so the 12 columns needed sit at offsets 2..13;
+    // out-of-image elements are zero filled) two tiles ahead, issued by thread 320 together with the tile's
+    // origin; nobody in stage 1 computes a global address or waits at a CTA barrier.  Four patch buffers: the TMA
+    // for tile j+2 overwrites the buffer of tile j-2, which every stage-1 thread finished reading before it arrived
+    // on a1_full(j-2) -- and thread 320 has since waited for conv1a(j-1), which needed all those arrivals.
+    auto issue_patch = [&](int t, int j) {
+      if (sid == 0) {
+        const int n = t / tiles_per_view, rem = t % tiles_per_view;
+        const int y0 = (rem / a.tiles_x) * 16, x0 = (rem % a.tiles_x) * 8;
+        sm.origin[j & 3] = make_int2(x0, y0);
+        mbar_expect_tx(patch_full(j & 3), 1280);
+        tma_load_3d(smem_u32(sm.patch[j & 3]), &tm_x, patch_full(j & 3), x0 - 4, y0 - 2, n);
       }
-      const Mat3 M = load_mat(a.mats + 9 * (a.shared_mats ? n % a.vpi : n));
-      const float* src = a.x + (long long)(n / a.vpi) * a.H * a.W;
-      float ix, iy;
-      warp_coord(M, a.lx.at(xx), a.ly.at(yy), a.W, a.H, ix, iy);
-      const Taps tp = make_taps(ix, iy);
-      r.v = bilinear(tp, a.W, a.H, [&](int sx, int sy) { return __ldg(src + (long long)sy * a.W + sx); });
-      r.valid = in_bounds(rintf(ix), rintf(iy), a.W, a.H) ? 1u : 0u;
-      return r;
     };
-    auto build = [&](PatchVal pv, int t, int buf, int pit) {  // patch -> K=16 im2col rows of the 180 halo pixels of tile t
+    auto build = [&](int j, int pit) {  // patch -> K=16 im2col rows of the 180 halo pixels of this CTA's j-th tile
       auto probe = [&](int slot) {
         if (a.dbg && blockIdx.x == 0 && pit >= 0 && pit < 64 && threadIdx.x == 320) a.dbg[pit * 16 + slot] = clock64();
       };
-      const int y0 = ((t % tiles_per_view) / a.tiles_x) * 16, x0 = ((t % tiles_per_view) % a.tiles_x) * 8;
-      if (sid < 240) {
-        sm.patch[buf][sid] = pv.v;
-        const int pr = sid / 12 - 2, pc = sid % 12 - 2;  // position inside the 16x8 tile
-        if (a.bits && pv.valid && pr >= 0 && pr < 16 && pc >= 0 && pc < 8) atomicOr(&sm.mrow[buf][pr], 1u << pc);
-      }
-      named_bar_sync(2, 256);
+      const int buf = j & 1;
+      mbar_wait(patch_full(j & 3), (j >> 2) & 1);
       probe(13);
-      if (a.bits && sid < 16) {
-        if (y0 + sid < a.H && x0 < a.W)
-          a.bits[((long long)(t / tiles_per_view) * a.H + y0 + sid) * (a.W >> 3) + (x0 >> 3)] = (uint8_t)sm.mrow[buf][sid];
-        sm.mrow[buf][sid] = 0u;
-      }
       if (sid < 180) {
-        const float* pp = sm.patch[buf] + (sid / 10) * 12 + sid % 10;  // tap (0,0) of halo pixel sid
+        const int2 org = sm.origin[j & 3];
+        const float* pp = sm.patch[j & 3] + (sid / 10) * 16 + sid % 10 + 2;  // tap (0,0) of halo pixel sid
         // conv1b zero-pads conv1a's OUTPUT: a halo pixel outside the image must come out as exactly 0, so its
         // whole im2col row is zeroed (its taps can reach inside the image), INCLUDING the two bias slots
-        const int hy = y0 - 1 + sid / 10, hx = x0 - 1 + sid % 10;
+        const int hy = org.y - 1 + sid / 10, hx = org.x - 1 + sid % 10;
         const bool inside = hy >= 0 && hy < a.H && hx >= 0 && hx < a.W;
         uint32_t pk[5];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const int k0 = 2 * k, k1 = 2 * k + 1;
-          const __nv_bfloat162 hh = __floats2bfloat162_rn(pp[(k0 / 3) * 12 + k0 % 3], pp[(k1 / 3) * 12 + k1 % 3]);
+          const __nv_bfloat162 hh = __floats2bfloat162_rn(pp[(k0 / 3) * 16 + k0 % 3], pp[(k1 / 3) * 16 + k1 % 3]);
           pk[k] = *reinterpret_cast<const uint32_t*>(&hh);
         }
-        const __nv_bfloat162 hh = __floats2bfloat162_rn(pp[2 * 12 + 2], 1.f);  // slot 9: bias head
+        const __nv_bfloat162 hh = __floats2bfloat162_rn(pp[2 * 16 + 2], 1.f);  // slot 9: bias head
         pk[4] = *reinterpret_cast<const uint32_t*>(&hh);
         if (!inside) pk[0] = pk[1] = pk[2] = pk[3] = pk[4] = 0u;
         const int h = sid >> 7, rr = sid & 127;
@@ -946,18 +794,19 @@ __global__ void __launch_bounds__(576, 1) conv1_fused_kernel(const __grid_consta
       probe(15);
     };
     int it = 0;
-    PatchVal pv{0.f, 0u};
     if ((int)blockIdx.x < a.ntiles) {
-      build(patch_load(blockIdx.x), blockIdx.x, 0, -1);
-      if ((int)(blockIdx.x + gridDim.x) < a.ntiles) pv = patch_load(blockIdx.x + gridDim.x);
+      issue_patch(blockIdx.x, 0);
+      if ((int)(blockIdx.x + gridDim.x) < a.ntiles) issue_patch(blockIdx.x + gridDim.x, 1);
+      if ((int)(blockIdx.x + 2 * gridDim.x) < a.ntiles) issue_patch(blockIdx.x + 2 * gridDim.x, 2);
+      build(0, -1);
     }
     for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x, ++it) {
 #define SPB_PROBE1(slot)                                                                                 \
   if (a.dbg && blockIdx.x == 0 && it < 64 && threadIdx.x == 320) a.dbg[it * 16 + (slot)] = clock64()
       SPB_PROBE1(5);
       if (t + (int)gridDim.x < a.ntiles) {
-        build(pv, t + gridDim.x, (it + 1) & 1, it);                                // im2col of tile it+1
-        if (t + 2 * (int)gridDim.x < a.ntiles) pv = patch_load(t + 2 * gridDim.x);  // prefetch for tile it+2
+        build(it + 1, it);                                                                   // im2col of tile it+1
+        if (t + 3 * (int)gridDim.x < a.ntiles) issue_patch(t + 3 * gridDim.x, it + 3);        // patch of tile it+3
       }
       SPB_PROBE1(6);
       const int buf = it & 1, ph = (it >> 1) & 1;
@@ -995,29 +844,53 @@ __global__ void __launch_bounds__(576, 1) conv1_fused_kernel(const __grid_consta
     }
   } else {
     // =========================== conv1b epilogue (warps 2..9): bias + ReLU + 2x2 max-pool + bf16 ===========
+    // The two warps of a TMEM quadrant (32 channels each) fill the 8 pooled pixels x 128 B of that quadrant in a
+    // SWIZZLE_128B staging tile and ONE TMA tensor store writes it: 8-lane 16-byte global stores cost a wavefront
+    // per lane in the pipe the tensor core reads its operands through; so do bias LDS -> biases live in registers.
     const int quad = warp & 3, chalf = (warp - 2) >> 2;
-    const int m = quad * 32 + lane, py = m >> 3, px = m & 7;
+    const bool owner = !(lane & 9);                          // even column, even row of the 2x2 window
+    const int p = (lane >> 4) * 4 + ((lane & 7) >> 1);       // pooled pixel of the quadrant (2 rows x 4 columns)
+    const bool issuer = chalf == 0 && lane == 0;
+    float bz[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) bz[j] = sm.bias2[chalf * 32 + j];
     int it = 0;
     for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x, ++it) {
       const int buf = it & 1, ph = (it >> 1) & 1;
       const int n = t / tiles_per_view, rem = t % tiles_per_view;
-      const int y = (rem / a.tiles_x) * 16 + py, x = (rem % a.tiles_x) * 8 + px;
+      const int y0 = (rem / a.tiles_x) * 16 + 4 * quad, x0 = (rem % a.tiles_x) * 8;
       if (a.dbg && blockIdx.x == 0 && it < 64 && threadIdx.x == 64) a.dbg[it * 16 + 10] = clock64();
       mbar_wait(acc2_full(buf), ph);
       if (a.dbg && blockIdx.x == 0 && it < 64 && threadIdx.x == 64) a.dbg[it * 16 + 11] = clock64();
       tc_fence_after();
       const uint32_t taddr = tmem_base + buf * 64 + chalf * 32 + ((uint32_t)(quad * 32) << 16);
-      const bool valid = y < a.H && x < a.W && !(px & 1) && !(py & 1);
-      const long long opix = ((long long)n * (a.H >> 1) + (y >> 1)) * (a.W >> 1) + (x >> 1);
       uint32_t v[32];
       tc_ld_nowait<32>(taddr, v);
       tc_wait_ld();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc2_empty(buf));
-      epi_bf16_32<true>(v, sm.bias2 + chalf * 32, valid, a.out + opix * 64 + chalf * 32);
+      uint32_t pk[16];
+      epi_pack32_regs<true>(v, bz, pk);
+      uint8_t* stg = sm.ostage[buf][quad];
+      if (owner) {
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4)
+          *reinterpret_cast<uint4*>(stg + p * 128 + (((chalf * 4 + q4) ^ (p & 7)) * 16)) =
+              make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      // the previous tile's store (other staging buffer) must have drained before the pair passes this barrier
+      // and goes on to overwrite that buffer
+      if (issuer) tma_store_wait_read<0>();
+      named_bar_sync(3 + quad, 64);
+      if (issuer) {
+        tma_store_4d(&tm_out, smem_u32(stg), 0, x0 >> 1, y0 >> 1, n);  // clipped at the image border
+        tma_store_commit();
+      }
       if (a.dbg && blockIdx.x == 0 && it < 64 && threadIdx.x == 64) a.dbg[it * 16 + 12] = clock64();
     }
+    if (issuer) tma_store_wait_read<0>();
   }
   tc_fence_before();
   __syncthreads();
@@ -1030,11 +903,7 @@ __global__ void __launch_bounds__(576, 1) conv1_fused_kernel(const __grid_consta
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode() {
+EncodeTiledFn get_encode() {
   static EncodeTiledFn fn = nullptr;
   if (!fn) {
     void* p = nullptr;
@@ -1067,7 +936,7 @@ static int encode_weight_map(CUtensorMap* tm, const LayerDev& L) {
   return SPB_OK;
 }
 
-static int encode_act_map(CUtensorMap* tm, const void* in, int B, int H, int W, int C, int boxw, int boxh) {
+int encode_act_map(CUtensorMap* tm, const void* in, int B, int H, int W, int C, int boxw, int boxh) {
   EncodeTiledFn enc = get_encode();
   if (!enc) {
     set_error("conv_tc: cuTensorMapEncodeTiled not available from the driver");
@@ -1128,35 +997,18 @@ extern "C" int spb_conv_tc_set_fuse1(int on) {
   return SPB_OK;
 }
 bool conv1_fused_enabled() { return g_fuse1 != 0; }
-// Homography warp + valid-mask bits produced inside conv1's stage 1 instead of by warp_bits_kernel.  Bit-identical
-// results, but the 4-tap gathers lengthen stage 1 (the critical producer of the fused block), so it is OFF by default.
-static int g_fuse_warp = 0;
-extern "C" int spb_conv_tc_set_fuse_warp(int on) {
-  g_fuse_warp = on ? 1 : 0;
-  return SPB_OK;
-}
-bool conv1_warp_fused_enabled() { return g_fuse1 != 0 && g_fuse_warp != 0; }
+
+bool conv1_fused_supports(int H, int W) { return !((H | W) & 1) && !(W & 3); }
 
 int conv1_fused(const LayerDev& L1a, const LayerDev& L1b, const float* x, __nv_bfloat16* out, int V, int H, int W,
-                const ViewSource* vs, cudaStream_t st) {
-  if ((H | W) & 1) {
-    set_error("conv1_fused: pooled block needs even H, W (got %dx%d)", H, W);
+                cudaStream_t st) {
+  if (!conv1_fused_supports(H, W)) {
+    set_error("conv1_fused: needs even H and W %% 4 == 0 (got %dx%d)", H, W);
     return SPB_EINVAL;
   }
   CUtensorMap tm_w2;
   memcpy(&tm_w2, L1b.tmap_w, sizeof(tm_w2));
   Conv1FusedArgs a;
-  a.x = x;
-  a.mats = vs ? vs->mats : nullptr;
-  a.bits = vs ? vs->bits : nullptr;
-  a.vpi = vs ? vs->vpi : 1;
-  a.shared_mats = vs ? vs->shared_mats : 0;
-  a.lx = Lin(W);
-  a.ly = Lin(H);
-  if (vs && (W & 7)) {
-    set_error("conv1_fused: warp mode needs W %% 8 == 0 (got %d)", W);
-    return SPB_EINVAL;
-  }
   a.w1a = L1a.w_tc;
   a.bias1 = L1a.bias;
   a.bias2 = L1b.bias;
@@ -1168,10 +1020,28 @@ int conv1_fused(const LayerDev& L1a, const LayerDev& L1b, const float* x, __nv_b
   a.tiles_y = ceil_div(H, 16);
   a.ntiles = V * a.tiles_x * a.tiles_y;
   a.dbg = g_conv1_dbg;
+  CUtensorMap tm_out, tm_x;
+  {
+    const int rc = encode_act_map(&tm_out, out, V, H / 2, W / 2, 64, 4, 2);
+    if (rc != SPB_OK) return rc;
+    // fp32 views [V,H,W]: box = the 16 x 20 patch under a halo block, zero filled outside the image
+    EncodeTiledFn enc = get_encode();
+    cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)V};
+    cuuint64_t strides[2] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4};
+    cuuint32_t box[3] = {16, 20, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    const CUresult r = enc(&tm_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(x), dims, strides, box, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("conv1_fused: cuTensorMapEncodeTiled(views %dx%dx%d) failed with CUresult %d", V, H, W, (int)r);
+      return SPB_ECUDA;
+    }
+  }
   const int smem = (int)sizeof(Conv1FusedSmem) + 1024;
   SPB_CHECK_CUDA(cudaFuncSetAttribute(conv1_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int grid = a.ntiles < kNumSMs ? a.ntiles : kNumSMs;
-  conv1_fused_kernel<<<grid, 576, smem, st>>>(tm_w2, a);
+  conv1_fused_kernel<<<grid, 576, smem, st>>>(tm_w2, tm_out, tm_x, a);
   SPB_CHECK_LAUNCH();
   return SPB_OK;
 }
@@ -1195,10 +1065,17 @@ extern "C" int spb_conv_tc_set_halo(int on) {
 template <class C>
 static int launch(const LayerDev& L, const __nv_bfloat16* in, void* out, int B, int H, int W, int out_mode,
                   cudaStream_t st) {
-  CUtensorMap tm_act, tm_wgt;
+  CUtensorMap tm_act, tm_wgt, tm_out;
   memcpy(&tm_wgt, L.tmap_w, sizeof(tm_wgt));
   int rc = encode_act_map(&tm_act, in, B, H, W, L.cin, C::P, C::R);
   if (rc != SPB_OK) return rc;
+  if (C::TMA_OUT) {  // one warp's quadrant: 4 rows x 8 pixels (pooled: 2 x 4) x 64 channels
+    rc = C::POOL ? encode_act_map(&tm_out, out, B, H / 2, W / 2, L.cout, 4, 2)
+                 : encode_act_map(&tm_out, out, B, H, W, L.cout, 8, 4);
+    if (rc != SPB_OK) return rc;
+  } else {
+    tm_out = tm_act;
+  }
   ConvArgs a;
   a.bias = L.bias;
   a.out = out;
@@ -1217,7 +1094,7 @@ static int launch(const LayerDev& L, const __nv_bfloat16* in, void* out, int B, 
   a.ntiles = B * a.tiles_x * a.tiles_y;
   SPB_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
   const int grid = a.ntiles < kNumSMs ? a.ntiles : kNumSMs;
-  conv_tc_kernel<C><<<grid, C::THREADS, C::SMEM, st>>>(tm_act, tm_wgt, a);
+  conv_tc_kernel<C><<<grid, C::THREADS, C::SMEM, st>>>(tm_act, tm_wgt, tm_out, a);
   SPB_CHECK_LAUNCH();
   return SPB_OK;
 }
@@ -1232,6 +1109,8 @@ int conv_tc(const LayerDev& L, const __nv_bfloat16* in, void* out, int B, int H,
     set_error("conv_tc: pooled layer needs even H, W (got %dx%d)", H, W);
     return SPB_EINVAL;
   }
+  if (L.w_s3 && conv_s3_enabled() && out_mode == 0)
+    return conv_s3(L, in, static_cast<__nv_bfloat16*>(out), B, H, W, st);
   const bool halo = g_halo_mode != 0;
 #define SPB_CONV(CIN, NPAD, KS, HALO, BRES, NA, NB, POOL, OUT) \
   launch<ConvCfg<CIN, NPAD, KS, HALO, BRES, NA, NB, POOL, OUT>>(L, in, out, B, H, W, out_mode, st)
@@ -1240,13 +1119,13 @@ int conv_tc(const LayerDev& L, const __nv_bfloat16* in, void* out, int B, int H,
     return halo ? SPB_CONV(64, 64, 3, true, true, 4, 0, false, 0) : SPB_CONV(64, 64, 3, false, true, 6, 0, false, 0);
   }
   if (L.ks == 3 && L.cin == 64 && L.cout_pad == 128)
-    return halo ? SPB_CONV(64, 128, 3, true, true, 3, 0, false, 0) : SPB_CONV(64, 128, 3, false, true, 4, 0, false, 0);
+    return halo ? SPB_CONV(64, 128, 3, true, true, 2, 0, false, 0) : SPB_CONV(64, 128, 3, false, true, 3, 0, false, 0);
   if (L.ks == 3 && L.cin == 128 && L.cout_pad == 128) {
     if (L.pool) return halo ? SPB_CONV(128, 128, 3, true, false, 4, 6, true, 0) : SPB_CONV(128, 128, 3, false, false, 6, 6, true, 0);
     return halo ? SPB_CONV(128, 128, 3, true, false, 4, 6, false, 0) : SPB_CONV(128, 128, 3, false, false, 6, 6, false, 0);
   }
   if (L.ks == 3 && L.cin == 128 && L.cout_pad == 256)
-    return halo ? SPB_CONV(128, 256, 3, true, false, 3, 4, false, 0) : SPB_CONV(128, 256, 3, false, false, 4, 4, false, 0);
+    return halo ? SPB_CONV(128, 256, 3, true, false, 2, 4, false, 0) : SPB_CONV(128, 256, 3, false, false, 3, 4, false, 0);
   if (L.ks == 1 && L.cin == 256 && L.cout_pad == 80 && out_mode == 1) return SPB_CONV(256, 80, 1, false, true, 6, 0, false, 1);
   if (L.ks == 1 && L.cin == 256 && L.cout_pad == 80 && out_mode == 3) return SPB_CONV(256, 80, 1, false, true, 6, 0, false, 3);
   if (L.ks == 1 && L.cin == 256 && L.cout_pad == 256 && out_mode == 2) return SPB_CONV(256, 256, 1, false, true, 4, 0, false, 2);

@@ -99,22 +99,17 @@ static int run_layer(const Net* net, int li, const void* in, void* out, int B, i
 }
 
 // semi: logits [B,Hc,Wc,65] (or NULL); probs: softmax probabilities [B,Hc,Wc,64] (or NULL); desc optional
-// vs != NULL (tcgen05 + fused first block only): x holds SOURCE images and the homography warp happens inside conv1
 static int forward(const Net* net, const float* x, int B, int H, int W, float* semi, float* probs, float* desc,
-                   void* ws, cudaStream_t st, const ViewSource* vs = nullptr) {
+                   void* ws, cudaStream_t st) {
   Workspace w(ws, B, H, W);
   int rc;
 #define RUN(li, in, out, h, wd, mode)                                     \
   if ((rc = run_layer(net, li, in, out, B, h, wd, mode, st)) != SPB_OK) return rc
-  if (net->impl == SPB_IMPL_TCGEN05 && conv1_fused_enabled()) {
+  if (net->impl == SPB_IMPL_TCGEN05 && conv1_fused_enabled() && conv1_fused_supports(H, W)) {
     // conv1a + conv1b + pool in one kernel: the 64-channel full-resolution activation never leaves the SM
     StageTimer tm(net, 1, st);
-    if ((rc = conv1_fused(net->layer[0], net->layer[1], x, w.buf1, B, H, W, vs, st)) != SPB_OK) return rc;
+    if ((rc = conv1_fused(net->layer[0], net->layer[1], x, w.buf1, B, H, W, st)) != SPB_OK) return rc;
   } else {
-    if (vs) {
-      set_error("forward: warp-fused input needs the tcgen05 fused first block");
-      return SPB_EINVAL;
-    }
     RUN(0, x, w.buf0, H, W, 0);
     RUN(1, w.buf0, w.buf1, H, W, 0);  // + pool -> H/2
   }
@@ -214,8 +209,19 @@ int spb_net_create(spb_net** out, const float* const* weights, const float* cons
       SPB_CHECK_CUDA(cudaMalloc(&L.w1a_f32, w1.size() * sizeof(float)));
       SPB_CHECK_CUDA(cudaMemcpy(L.w1a_f32, w1.data(), w1.size() * sizeof(float), cudaMemcpyHostToDevice));
     } else {
-      const int rc = conv_tc_prepare(L);
+      int rc = conv_tc_prepare(L);
       if (rc != SPB_OK) return rc;
+      if (S.ks == 3 && S.cin == 64 && S.cout == 64) {
+        std::vector<__nv_bfloat16> w3((size_t)576 * 64);
+        for (int r = 0; r < 3; ++r)
+          for (int sx = 0; sx < 3; ++sx)
+            for (int co = 0; co < 64; ++co)
+              for (int ci = 0; ci < 64; ++ci)
+                w3[((size_t)(r * 3 + sx) * 64 + co) * 64 + ci] = wt[(size_t)co * Kpad + (size_t)(r * 3 + sx) * 64 + ci];
+        SPB_CHECK_CUDA(cudaMalloc(&L.w_s3, w3.size() * 2));
+        SPB_CHECK_CUDA(cudaMemcpy(L.w_s3, w3.data(), w3.size() * 2, cudaMemcpyHostToDevice));
+        if ((rc = conv_s3_prepare(L)) != SPB_OK) return rc;
+      }
     }
   }
   *out = reinterpret_cast<spb_net*>(net);
@@ -231,7 +237,9 @@ int spb_net_destroy(spb_net* h) {
     cudaFree(L.w_simt);
     cudaFree(L.w_tc);
     cudaFree(L.w1a_f32);
+    cudaFree(L.w_s3);
     free(L.tmap_w);
+    free(L.tmap_w3);
   }
   for (int i = 0; i < net->nrecs; ++i) {
     cudaEventDestroy(net->recs[i].a);
@@ -348,23 +356,16 @@ int spb_ha_heatmap_sums_batch(spb_net* h, const float* imgs, const float* mats_u
       const long long moff = shared_mats ? 9LL * n0 : 9LL * ((long long)b0 * N + n0);
       // per-image matrix sets are only contiguous over a whole image: view chunks imply bg == 1
       int rc;
-      if (tc && conv1_warp_fused_enabled()) {
-        // warp + valid mask are fused into the first conv block: source images go straight into the network
-        ViewSource vs = {mats_fwd + moff, bits, nn, shared_mats};
-        rc = forward(net, imgs + (long long)b0 * H * W, bg * nn, H, W, nullptr, probs, nullptr, base + L.net, st, &vs);
-        if (rc != SPB_OK) return rc;
-      } else {
-        {
-          StageTimer tm(net, 12, st);
-          rc = warp_with_mask_bits(imgs + (long long)b0 * H * W, mats_fwd + moff, warped, bits, bg * nn, nn,
-                                   shared_mats, H, W, st);
-        }
-        if (rc != SPB_OK) return rc;
-        // the detector head writes softmax probabilities directly (tcgen05 epilogue); the validation path goes
-        // through logits + a softmax kernel
-        rc = forward(net, warped, bg * nn, H, W, tc ? nullptr : semi, probs, nullptr, base + L.net, st);
-        if (rc != SPB_OK) return rc;
+      {
+        StageTimer tm(net, 12, st);
+        rc = warp_with_mask_bits(imgs + (long long)b0 * H * W, mats_fwd + moff, warped, bits, bg * nn, nn, shared_mats,
+                                 H, W, st);
       }
+      if (rc != SPB_OK) return rc;
+      // the detector head writes softmax probabilities directly (tcgen05 epilogue); the validation path goes
+      // through logits + a softmax kernel
+      rc = forward(net, warped, bg * nn, H, W, tc ? nullptr : semi, probs, nullptr, base + L.net, st);
+      if (rc != SPB_OK) return rc;
       {
         StageTimer tm(net, 13, st);
         rc = aggregate_probs(probs, bits, mats_unwarp + moff, shared_mats, bg, nn, H, W,

@@ -14,6 +14,8 @@ struct LayerDev {
   __nv_bfloat16* w_tc;         // bf16 [cout_pad][tap*cin]   (K-major rows for the UMMA B operand)
   float* w1a_f32;              // conv1a only: bf16-rounded weights as fp32 [9][64]
   void* tmap_w;                // host copy of the CUtensorMap for w_tc (conv_tc.cu), 128 B
+  __nv_bfloat16* w_s3;         // 64->64 3x3 layers: bf16 [r][s][co][ci] (conv_s3.cu: column taps stacked along N)
+  void* tmap_w3;               // host copy of the CUtensorMap for w_s3
 };
 
 constexpr int kNumStages = 16;  // 0..11 layers, 12 warp, 13 aggregate
@@ -46,20 +48,19 @@ int aggregate_probs(const float* probs, const uint8_t* bits, const float* mats_u
 
 // conv_tc.cu (tcgen05 / TMEM / TMA)
 int conv1a_tc(const LayerDev& L, const float* x, __nv_bfloat16* out, int B, int H, int W, cudaStream_t st);
-// Homography-warp mode of the fused first block: the kernel reads SOURCE images and warps on the fly.
-struct ViewSource {
-  const float* mats;  // forward homographies (sample['inv_homographies'])
-  uint8_t* bits;      // valid-mask bits out [V,H,W/8]
-  int vpi;            // views per source image
-  int shared_mats;    // matrices shared by all images (index n % vpi) or per image (index n)
-};
 bool conv1_fused_enabled();
-bool conv1_warp_fused_enabled();
+bool conv1_fused_supports(int H, int W);  // even H, W % 4 == 0 (TMA row pitch)
 int conv1_fused(const LayerDev& L1a, const LayerDev& L1b, const float* x, __nv_bfloat16* out, int V, int H, int W,
-                const ViewSource* vs, cudaStream_t st);
+                cudaStream_t st);
 int conv_tc_prepare(LayerDev& L);  // builds the weight tensor map after w_tc is uploaded
 // out_mode: 0 bf16 NHWC, 1 fp32 rows (cout channels), 2 fp32 rows L2-normalised, 3 softmax probabilities
 // (convPb only: fp32 [.,64], dustbin dropped)
 int conv_tc(const LayerDev& L, const __nv_bfloat16* in, void* out, int B, int H, int W, int out_mode, cudaStream_t st);
+
+
+// conv_s3.cu (64 -> 64, N = 192 column-tap stacking)
+bool conv_s3_enabled();
+int conv_s3_prepare(LayerDev& L);  // after w_s3 is uploaded
+int conv_s3(const LayerDev& L, const __nv_bfloat16* in, __nv_bfloat16* out, int B, int H, int W, cudaStream_t st);
 
 }  // namespace spb

@@ -79,6 +79,31 @@ def test_tcgen05_layer_vs_reference(net, li, B, H, W, halo):
     assert (tc - simt).abs().max().item() <= (3.2e-2 if li not in (9, 11) else 1e-4)
 
 
+@pytest.mark.parametrize("li,B,H,W", [(2, 3, 24, 30), (3, 2, 16, 28), (1, 1, 8, 14), (2, 1, 9, 17), (3, 5, 40, 58),
+                                      (2, 2, 120, 160), (3, 2, 120, 160), (2, 1, 3, 2)])
+def test_s3_column_stacked_kernel(net, li, B, H, W):
+    """64->64 layers on the N=192 column-tap-stacked kernel (conv_s3.cu): ragged tiles (W % 14, H % 8), pooling,
+    vs torch fp32, the CUDA-core kernel and the shifted-window tcgen05 kernel."""
+    from pytorch_superpoint_b200 import _lib
+    L = _lib.lib()
+    torch.manual_seed(li * 11 + W)
+    x = (torch.randn(B, H, W, 64, device="cuda") * 0.5).to(torch.bfloat16).contiguous()
+    params = O.canonical_params(O.synthetic_state_dict("gauss2", seed=1))
+    ref = _ref_layer(li, x, params)
+    simt = _layer(net, li, x, B, H, W, "simt").float()
+    try:
+        L.spb_conv_tc_set_s3(0)
+        win = _layer(net, li, x, B, H, W, "tcgen05").float()
+        L.spb_conv_tc_set_s3(1)
+        s3 = _layer(net, li, x, B, H, W, "tcgen05").float()
+    finally:
+        L.spb_conv_tc_set_s3(1)
+    assert torch.isfinite(s3).all()
+    assert (s3 - ref).abs().max().item() < 3e-2
+    assert (s3 - simt).abs().max().item() <= 3.2e-2 and (s3 - win).abs().max().item() <= 3.2e-2
+    assert (s3 != win).float().mean().item() < 0.02  # same products, different fp32 summation order: rare 1-ulp flips
+
+
 @pytest.mark.parametrize("B,H,W", [(1, 16, 8), (3, 24, 40), (2, 240, 320), (5, 30, 52)])
 def test_conv1a_tensor_core_vs_simt(net, B, H, W):
     """conv1a as a K=16 im2col MMA: same bf16 numerics as the CUDA-core kernel, incl. ragged last tile."""
@@ -177,6 +202,7 @@ def test_conv1_fused_block_equals_two_kernels(net, B, H, W):
     x = torch.rand(B, 1, H, W, device="cuda", generator=torch.Generator("cuda").manual_seed(W))
     net.set_impl("tcgen05")
     try:
+        L.spb_conv_tc_set_s3(0)  # the unfused conv1b must use the same (shifted-window) accumulation order
         L.spb_conv_tc_set_fuse1(0)
         s0, d0 = net.forward_nhwc(x)
         s0, d0 = s0.clone(), d0.clone()
@@ -184,31 +210,7 @@ def test_conv1_fused_block_equals_two_kernels(net, B, H, W):
         s1, d1 = net.forward_nhwc(x)
     finally:
         L.spb_conv_tc_set_fuse1(1)
+        L.spb_conv_tc_set_s3(1)
     assert torch.isfinite(s1).all()
     assert (s0 - s1).abs().max().item() <= 1e-5  # same bf16 intermediate, same accumulation order
     assert (d0 - d1).abs().max().item() <= 1e-6
-
-
-@pytest.mark.parametrize("H,W,N", [(48, 64, 6), (240, 320, 12), (40, 24, 3)])
-def test_ha_warp_fused_into_conv1_equals_separate_warp_kernel(H, W, N):
-    """HA path with the homography warp + valid-mask bits produced inside the fused first conv block
-    == HA path with the stand-alone warp kernel and the two-kernel first block."""
-    from pytorch_superpoint_b200 import SuperPointNet_b200, _lib, make_ha_homographies
-    L = _lib.lib()
-    n = SuperPointNet_b200()
-    n.load_state_dict(O.synthetic_state_dict("gauss2", seed=2))
-    B = 2
-    imgs = torch.rand(B, H, W, device="cuda", generator=torch.Generator("cuda").manual_seed(H + N))
-    mu, mf = make_ha_homographies(N, seed=H)
-    mu, mf = torch.from_numpy(mu).cuda(), torch.from_numpy(mf).cuda()
-    try:
-        L.spb_conv_tc_set_fuse1(0)
-        ref = n.ha_heatmap_sums_batch(imgs, mu, mf).clone()
-        L.spb_conv_tc_set_fuse1(1)
-        L.spb_conv_tc_set_fuse_warp(1)
-        out = n.ha_heatmap_sums_batch(imgs, mu, mf).clone()
-    finally:
-        L.spb_conv_tc_set_fuse1(1)
-        L.spb_conv_tc_set_fuse_warp(0)
-    assert torch.equal(out[:, 1], ref[:, 1])                       # sum of masks: identical bits
-    assert (out[:, 0] - ref[:, 0]).abs().max().item() <= 1e-6      # sum of heat*mask

@@ -93,7 +93,26 @@ __global__ void __launch_bounds__(320, 1) bench(Res* res, int iters, int pitch) 
       const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
       const long long t0 = clock64();
       for (int it = 0; it < iters; ++it) {
-        const uint32_t d = tmem + (N <= 128 ? (it & 1) * N : 0);
+        const uint32_t d = tmem + ((N <= 128 || (mode & 16)) ? (it & 1) * N : 0);
+        if (mode & 16) {  // conv_s3 tile: 12 MMAs then 24 row shifts of the partial-sum blocks
+          if (elect_one()) {
+#pragma unroll
+            for (int g = 0; g < 12; ++g) {
+              const uint32_t off = ((g / 4) * pitch) * 128;
+              const uint64_t ad = hi_a | (uint64_t)(((a0 + off) >> 4) | (1u << 16));
+              const uint64_t bd = hi_b | (uint64_t)((b0 >> 4) | (1u << 16));
+              tc_mma_ss(d, ad + 2 * (g & 3), bd + 2 * (g & 3), idesc, g != 0);
+            }
+            if (mode & 32) {
+#pragma unroll
+              for (int c8 = 64; c8 < 192; c8 += 8) asm volatile("tcgen05.shift.cta_group::1.down [%0];" ::"r"(d + c8) : "memory");
+#pragma unroll
+              for (int c8 = 128; c8 < 192; c8 += 8) asm volatile("tcgen05.shift.cta_group::1.down [%0];" ::"r"(d + c8) : "memory");
+            }
+          }
+          __syncwarp();
+          continue;
+        }
 #pragma unroll
         for (int tap = 0; tap < 9; ++tap) {
           const uint32_t off = ((tap / 3) * pitch + tap % 3) * 128;
@@ -202,6 +221,8 @@ int main() {
     run<64, 2>("SS + 8 warps tcgen05.ld", it, 10, grid);
     run<64, 6>("SS + 8 warps ld + st.shared", it, 10, grid);
     run<192, 6>("SS + 8 warps ld + st.shared", it, 32, grid);
+    run<192, 16>("s3 tile: 12 MMAs (x3 = per 36)", it, 16, grid);
+    run<192, 48>("s3 tile: 12 MMAs + 24 shifts (x3)", it, 16, grid);
     run<64, 2>("ld only", 0, 10, grid);
     run<64, 6>("ld + st.shared only", 0, 10, grid);
   }
