@@ -736,6 +736,8 @@ __global__ void __launch_bounds__(576, 1) conv1_fused_kernel(const __grid_consta
         __syncwarp();
       }
       SPB_PROBE(4);
+      // (issuing conv1a(k+1) in the MIDDLE of conv1b instead was measured 3x slower: the issuer then stalls with
+      // the token in hand whenever stage 1 is not ahead, and both issuers end up waiting on each other)
       if (t + 2 * (int)gridDim.x < a.ntiles) issue_conv1a(k + 1);
     }
   } else if (warp >= 10) {
@@ -750,21 +752,31 @@ __global__ void __launch_bounds__(576, 1) conv1_fused_kernel(const __grid_consta
     // origin; nobody in stage 1 computes a global address or waits at a CTA barrier.  Four patch buffers: the TMA
     // for tile j+2 overwrites the buffer of tile j-2, which every stage-1 thread finished reading before it arrived
     // on a1_full(j-2) -- and thread 320 has since waited for conv1a(j-1), which needed all those arrivals.
-    auto issue_patch = [&](int t, int j) {
-      if (sid == 0) {
-        const int n = t / tiles_per_view, rem = t % tiles_per_view;
-        const int y0 = (rem / a.tiles_x) * 16, x0 = (rem % a.tiles_x) * 8;
-        sm.origin[j & 3] = make_int2(x0, y0);
-        mbar_expect_tx(patch_full(j & 3), 1280);
-        tma_load_3d(smem_u32(sm.patch[j & 3]), &tm_x, patch_full(j & 3), x0 - 4, y0 - 2, n);
+    // Warp 10 walks the tile sequence of this CTA incrementally (no divisions) and one elected lane issues.
+    const int tpv = tiles_per_view;
+    const int dgn = (int)gridDim.x / tpv, dgr = (int)gridDim.x % tpv;
+    const int dgy = dgr / a.tiles_x, dgx = dgr % a.tiles_x;
+    int pn = (int)blockIdx.x / tpv, pty = ((int)blockIdx.x % tpv) / a.tiles_x, ptx = ((int)blockIdx.x % tpv) % a.tiles_x;
+    auto issue_patch = [&](int j) {  // patch of this CTA's j-th tile = the tile the walker stands on; then advance
+      if (warp == 10) {
+        if (elect_one()) {
+          sm.origin[j & 3] = make_int2(ptx * 8, pty * 16);
+          mbar_expect_tx(patch_full(j & 3), 1280);
+          tma_load_3d(smem_u32(sm.patch[j & 3]), &tm_x, patch_full(j & 3), ptx * 8 - 4, pty * 16 - 2, pn);
+        }
+        __syncwarp();
+        ptx += dgx;
+        if (ptx >= a.tiles_x) { ptx -= a.tiles_x; ++pty; }
+        pty += dgy;
+        if (pty >= a.tiles_y) { pty -= a.tiles_y; ++pn; }
+        pn += dgn;
       }
     };
     auto build = [&](int j, int pit) {  // patch -> K=16 im2col rows of the 180 halo pixels of this CTA's j-th tile
       auto probe = [&](int slot) {
         if (a.dbg && blockIdx.x == 0 && pit >= 0 && pit < 64 && threadIdx.x == 320) a.dbg[pit * 16 + slot] = clock64();
       };
-      const int buf = j & 1;
-      mbar_wait(patch_full(j & 3), (j >> 2) & 1);
+      const int buf = j & 1;  // (the caller has waited for patch_full(j & 3))
       probe(13);
       if (sid < 180) {
         const int2 org = sm.origin[j & 3];
@@ -795,24 +807,31 @@ __global__ void __launch_bounds__(576, 1) conv1_fused_kernel(const __grid_consta
     };
     int it = 0;
     if ((int)blockIdx.x < a.ntiles) {
-      issue_patch(blockIdx.x, 0);
-      if ((int)(blockIdx.x + gridDim.x) < a.ntiles) issue_patch(blockIdx.x + gridDim.x, 1);
-      if ((int)(blockIdx.x + 2 * gridDim.x) < a.ntiles) issue_patch(blockIdx.x + 2 * gridDim.x, 2);
+      issue_patch(0);
+      if ((int)(blockIdx.x + gridDim.x) < a.ntiles) issue_patch(1);
+      if ((int)(blockIdx.x + 2 * gridDim.x) < a.ntiles) issue_patch(2);
+      mbar_wait(patch_full(0), 0);
       build(0, -1);
     }
     for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x, ++it) {
 #define SPB_PROBE1(slot)                                                                                 \
   if (a.dbg && blockIdx.x == 0 && it < 64 && threadIdx.x == 320) a.dbg[it * 16 + (slot)] = clock64()
       SPB_PROBE1(5);
-      if (t + (int)gridDim.x < a.ntiles) {
-        build(it + 1, it);                                                                   // im2col of tile it+1
-        if (t + 3 * (int)gridDim.x < a.ntiles) issue_patch(t + 3 * gridDim.x, it + 3);        // patch of tile it+3
+      const int buf = it & 1, ph = (it >> 1) & 1;
+      const bool has_next = t + (int)gridDim.x < a.ntiles;
+      if (has_next) {
+        // im2col of tile it+1 FIRST, and without waiting for anything conv1a(it) related: conv1a(it+1) then has a
+        // whole iteration to get through the MMA queue before its accumulator is needed
+        mbar_wait(patch_full((it + 1) & 3), ((it + 1) >> 2) & 1);
+        build(it + 1, it);
+        if (t + 3 * (int)gridDim.x < a.ntiles) issue_patch(it + 3);   // patch of tile it+3
       }
       SPB_PROBE1(6);
-      const int buf = it & 1, ph = (it >> 1) & 1;
-      mbar_wait(acc1_full(buf), ph);
-      SPB_PROBE1(7);
-      mbar_wait(a2_empty(buf), ph ^ 1);
+      // the two barriers epi1 depends on are polled by two different lanes at once (a satisfied mbarrier wait still
+      // costs a ~200-cycle shared-memory round trip under load)
+      if (lane == 0) mbar_wait(acc1_full(buf), ph);
+      if (lane == 1) mbar_wait(a2_empty(buf), ph ^ 1);
+      __syncwarp();
       SPB_PROBE1(8);
       tc_fence_after();
       uint32_t v[2][32];

@@ -21,10 +21,10 @@ for it in range(8, 14):
 import statistics
 per = [int(d[i + 1, 5] - d[i, 5]) for i in range(10, 60)]
 print("S1 period median", statistics.median(per))
-for a, b, nm in [(5, 13, "s1 patch store + named barrier"), (13, 14, "s1 im2col lds/sts"), (14, 15, "s1 fence+arrive"),
-                 (15, 6, "s1 prefetch issue"), (6, 7, "s1 wait acc1_full"), (7, 8, "s1 wait a2_empty"),
-                 (8, 9, "s1 epi1"), (0, 1, "mma wait acc2_empty"), (1, 2, "mma wait a2_full"), (2, 3, "mma wait token"),
-                 (3, 4, "mma issue conv1b"), (10, 11, "e2 wait acc2_full"), (11, 12, "e2 work")]:
+for a, b, nm in [(5, 13, "s1 wait patch"), (13, 14, "s1 im2col lds/sts"),
+                 (14, 15, "s1 fence+arrive"), (15, 6, "s1 patch issue"), (6, 8, "s1 2 waits in parallel"), (8, 9, "s1 epi1"), (0, 1, "mma wait acc2_empty"),
+                 (1, 2, "mma wait a2_full"), (2, 3, "mma wait token"), (3, 4, "mma issue conv1b"),
+                 (10, 11, "e2 wait acc2_full"), (11, 12, "e2 work")]:
     v = [int(d[i, b] - d[i, a]) for i in range(10, 60)]
     print(f"{nm:32s} median {statistics.median(v):8.0f}  max {max(v)}")
 v = [int(d[i + 2, 0] - d[i, 4]) for i in range(10, 58)]
