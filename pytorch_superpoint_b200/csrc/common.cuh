@@ -72,8 +72,10 @@ __device__ __forceinline__ float hrow(const Mat3& M, int r, float u, float v) {
 __device__ __forceinline__ void warp_coord(const Mat3& M, float u, float v, int W, int H, float& ix, float& iy) {
   const float X = hrow(M, 0, u, v), Y = hrow(M, 1, u, v), Z = hrow(M, 2, u, v);
   const float gx = __fdiv_rn(X, Z), gy = __fdiv_rn(Y, Z);
-  ix = __fmul_rn(__fdiv_rn(__fadd_rn(gx, 1.f), 2.f), (float)(W - 1));
-  iy = __fmul_rn(__fdiv_rn(__fadd_rn(gy, 1.f), 2.f), (float)(H - 1));
+  // (g + 1) / 2: halving is exact in binary floating point (and rounds identically in the subnormal range), so the
+  // multiplication by 0.5 is bit-identical to the reference's division and saves two IEEE division sequences
+  ix = __fmul_rn(__fmul_rn(__fadd_rn(gx, 1.f), 0.5f), (float)(W - 1));
+  iy = __fmul_rn(__fmul_rn(__fadd_rn(gy, 1.f), 0.5f), (float)(H - 1));
 }
 
 __device__ __forceinline__ bool in_bounds(float xf, float yf, int W, int H) {
@@ -113,6 +115,25 @@ __device__ __forceinline__ float bilinear(const Taps& t, int W, int H, F&& fetch
   if (in_bounds(t.x1, t.y0, W, H)) acc = __fadd_rn(acc, __fmul_rn(fetch((int)t.x1, (int)t.y0), t.w_ne));
   if (in_bounds(t.x0, t.y1, W, H)) acc = __fadd_rn(acc, __fmul_rn(fetch((int)t.x0, (int)t.y1), t.w_sw));
   if (in_bounds(t.x1, t.y1, W, H)) acc = __fadd_rn(acc, __fmul_rn(fetch((int)t.x1, (int)t.y1), t.w_se));
+  return acc;
+}
+
+// The same 4-tap sample with the shared work hoisted: two column and two row validity tests, two float->int
+// conversions, one row-base multiply.  Identical arithmetic (same products, same order of the additions, invalid
+// taps skipped), so it is bit-identical to bilinear(make_taps(..)).  fetch(int offset) reads element y*W + x.
+template <class F>
+__device__ __forceinline__ float bilinear_fast(const Taps& t, int W, int H, F&& fetch) {
+  const float wm = (float)(W - 1), hm = (float)(H - 1);
+  const bool vx0 = t.x0 >= 0.f && t.x0 <= wm, vx1 = t.x1 >= 0.f && t.x1 <= wm;
+  const bool vy0 = t.y0 >= 0.f && t.y0 <= hm, vy1 = t.y1 >= 0.f && t.y1 <= hm;
+  // clamp before converting so that the offsets of skipped taps stay finite; only valid taps are fetched
+  const int xi = (int)fminf(fmaxf(t.x0, -1.f), wm), yi = (int)fminf(fmaxf(t.y0, -1.f), hm);
+  const int o = yi * W + xi;
+  float acc = 0.f;
+  if (vx0 && vy0) acc = __fadd_rn(acc, __fmul_rn(fetch(o), t.w_nw));
+  if (vx1 && vy0) acc = __fadd_rn(acc, __fmul_rn(fetch(o + 1), t.w_ne));
+  if (vx0 && vy1) acc = __fadd_rn(acc, __fmul_rn(fetch(o + W), t.w_sw));
+  if (vx1 && vy1) acc = __fadd_rn(acc, __fmul_rn(fetch(o + W + 1), t.w_se));
   return acc;
 }
 

@@ -238,6 +238,7 @@ __global__ void __launch_bounds__(256) agg_probs_kernel(const float* __restrict_
   bits += (long long)b * N * H * Wc;
   if (!shared_mats) mu += (long long)b * N * 9;
   const float u = lx.at(x), v = ly.at(y);
+  const float wm = (float)(W - 1), hm = (float)(H - 1);
   float num = 0.f, den = 0.f;
   for (int n = g; n < N; n += G) {
     const Mat3 M = load_mat(mu + 9 * n);
@@ -246,19 +247,28 @@ __global__ void __launch_bounds__(256) agg_probs_kernel(const float* __restrict_
     const Taps tp = make_taps(ix, iy);
     const float* pn = probs + (long long)n * Hc * Wc * 64;
     const uint8_t* bn = bits + (long long)n * H * Wc;
+    // shared work of the four taps hoisted (validity per column / row, one float->int per axis, the cell-major
+    // offsets split into a row part and a column part); same products and the same order of additions as
+    // tap-by-tap evaluation -> bit-identical sums
+    const bool vx0 = tp.x0 >= 0.f && tp.x0 <= wm, vx1 = tp.x1 >= 0.f && tp.x1 <= wm;
+    const bool vy0 = tp.y0 >= 0.f && tp.y0 <= hm, vy1 = tp.y1 >= 0.f && tp.y1 <= hm;
+    const int x0 = (int)fminf(fmaxf(tp.x0, -1.f), wm), y0 = (int)fminf(fmaxf(tp.y0, -1.f), hm);
+    const int x1 = x0 + 1, y1 = y0 + 1;
+    const int cx0 = (x0 >> 3) * 64 + (x0 & 7), cx1 = (x1 >> 3) * 64 + (x1 & 7);
+    const int ry0 = (y0 >> 3) * Wc * 64 + ((y0 & 7) << 3), ry1 = (y1 >> 3) * Wc * 64 + ((y1 & 7) << 3);
+    const int by0 = y0 * Wc, by1 = y1 * Wc;
     float a = 0.f, b = 0.f;
-    auto tap = [&](float xf, float yf, float w) {
-      if (!in_bounds(xf, yf, W, H)) return;
-      const int xx = (int)xf, yy = (int)yf;
-      const float m = (float)((__ldg(bn + yy * Wc + (xx >> 3)) >> (xx & 7)) & 1);
-      const float pr = __ldg(pn + ((yy >> 3) * Wc + (xx >> 3)) * 64 + ((yy & 7) << 3 | (xx & 7)));
+    auto tap = [&](bool ok, int boff, int xx, int poff, float w) {
+      if (!ok) return;
+      const float m = (float)((__ldg(bn + boff + (xx >> 3)) >> (xx & 7)) & 1);
+      const float pr = __ldg(pn + poff);
       a = __fadd_rn(a, __fmul_rn(__fmul_rn(pr, m), w));
       b = __fadd_rn(b, __fmul_rn(m, w));
     };
-    tap(tp.x0, tp.y0, tp.w_nw);
-    tap(tp.x1, tp.y0, tp.w_ne);
-    tap(tp.x0, tp.y1, tp.w_sw);
-    tap(tp.x1, tp.y1, tp.w_se);
+    tap(vx0 && vy0, by0, x0, ry0 + cx0, tp.w_nw);
+    tap(vx1 && vy0, by0, x1, ry0 + cx1, tp.w_ne);
+    tap(vx0 && vy1, by1, x0, ry1 + cx0, tp.w_sw);
+    tap(vx1 && vy1, by1, x1, ry1 + cx1, tp.w_se);
     num = __fadd_rn(num, a);
     den = __fadd_rn(den, b);
   }

@@ -64,46 +64,46 @@ __global__ void __launch_bounds__(256) warp_kernel(const float* __restrict__ img
 // (utils/utils.py:696 uses the same grid and matrices as the image warp, datasets/Coco.py:279-282), packed one
 // bit per pixel: bits[(n*H + y)*(W/8) + x/8] bit (x%8).  Needs W % 8 == 0.
 // View n belongs to image n / vpi; its matrix is mats[n] (per-image sets, contiguous) or mats[n % vpi] (shared).
+// Grid: blockIdx.y = view, blockIdx.x * 256 threads over the (row, 4-pixel group) pairs of that view -- the view's
+// matrix is block-uniform and no thread divides 64-bit indices (those divisions were a quarter of the instructions).
 __global__ void __launch_bounds__(256) warp_bits_kernel(const float* __restrict__ img, const float* __restrict__ mats,
-                                                        float* __restrict__ out, uint8_t* __restrict__ bits, int N,
-                                                        int vpi, int shared_mats, int H, int W, Lin lx, Lin ly) {
-  const int Wq = W >> 2;
-  const long long total = (long long)N * H * Wq;
-  const int lane = threadIdx.x & 31;
-  for (long long base = blockIdx.x * 256LL + (threadIdx.x & ~31); base < total; base += (long long)gridDim.x * 256) {
-    const long long t = base + lane;
-    const bool in = t < total;
-    const long long tt = in ? t : total - 1;
-    const int xq = (int)(tt % Wq);
-    const int y = (int)((tt / Wq) % H);
-    const int n = (int)(tt / ((long long)Wq * H));
-    const Mat3 M = load_mat(mats + 9 * (shared_mats ? n % vpi : n));
-    const float* src = img + (long long)(n / vpi) * H * W;
-    const float v = ly.at(y);
-    float r[4];
-    unsigned nib = 0;
+                                                        float* __restrict__ out, uint8_t* __restrict__ bits, int vpi,
+                                                        int shared_mats, int H, int W, Lin lx, Lin ly) {
+  const unsigned Wq = (unsigned)W >> 2, per_view = (unsigned)H * Wq;
+  const int lane = threadIdx.x & 31, n = blockIdx.y;
+  const unsigned t = blockIdx.x * 256u + threadIdx.x;
+  const bool in = t < per_view;
+  const unsigned tt = in ? t : per_view - 1;
+  const int y = (int)(tt / Wq), xq = (int)(tt - (unsigned)y * Wq);
+  const Mat3 M = load_mat(mats + 9 * (shared_mats ? n % vpi : n));
+  const float* src = img + (long long)(n / vpi) * H * W;
+  const float v = ly.at(y);
+  float r[4];
+  unsigned nib = 0;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float ix, iy;
-      warp_coord(M, lx.at(xq * 4 + j), v, W, H, ix, iy);
-      const Taps tp = make_taps(ix, iy);
-      r[j] = bilinear(tp, W, H, [&](int xx, int yy) { return __ldg(src + (long long)yy * W + xx); });
-      nib |= (in_bounds(rintf(ix), rintf(iy), W, H) ? 1u : 0u) << j;
-    }
-    const unsigned hi = __shfl_down_sync(0xffffffffu, nib, 1);
-    if (in) {
-      *reinterpret_cast<float4*>(out + ((long long)n * H + y) * W + xq * 4) = make_float4(r[0], r[1], r[2], r[3]);
-      if (!(xq & 1)) bits[((long long)n * H + y) * (W >> 3) + (xq >> 1)] = (uint8_t)(nib | (hi << 4));
-    }
+  for (int j = 0; j < 4; ++j) {
+    float ix, iy;
+    warp_coord(M, lx.at(xq * 4 + j), v, W, H, ix, iy);
+    const Taps tp = make_taps(ix, iy);
+    r[j] = bilinear_fast(tp, W, H, [&](int o) { return __ldg(src + o); });
+    nib |= (in_bounds(rintf(ix), rintf(iy), W, H) ? 1u : 0u) << j;
+  }
+  const unsigned hi = __shfl_down_sync(0xffffffffu, nib, 1);
+  if (in) {
+    const long long row = (long long)n * H + y;
+    *reinterpret_cast<float4*>(out + row * W + xq * 4) = make_float4(r[0], r[1], r[2], r[3]);
+    if (!(xq & 1)) bits[row * (W >> 3) + (xq >> 1)] = (uint8_t)(nib | (hi << 4));
   }
 }
 
 int warp_with_mask_bits(const float* img, const float* mats, float* out, uint8_t* bits, int N, int vpi,
                         int shared_mats, int H, int W, cudaStream_t st) {
-  const long long total = (long long)N * H * (W / 4);
-  int blocks = ceil_div(total, 256);
-  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
-  warp_bits_kernel<<<blocks, 256, 0, st>>>(img, mats, out, bits, N, vpi, shared_mats, H, W, Lin(W), Lin(H));
+  if (N > 65535) {
+    set_error("warp_with_mask_bits: %d views in one launch (max 65535)", N);
+    return SPB_EINVAL;
+  }
+  dim3 grid(ceil_div((long long)H * (W / 4), 256), N);
+  warp_bits_kernel<<<grid, 256, 0, st>>>(img, mats, out, bits, vpi, shared_mats, H, W, Lin(W), Lin(H));
   SPB_CHECK_LAUNCH();
   return SPB_OK;
 }
