@@ -108,6 +108,15 @@ int spb_sample_desc_from_points(const float* coarse, int nhwc, const float* pts,
 int spb_soft_argmax_points(const float* heat, int H, int W, const float* pts, const int* count, int K,
                            int patch_size, float* dxdy, void* stream);
 
+/* NEXT row f-1 -- models/model_wrap.py:437-480 `PointTracker.nn_match_two_way`: desc1 [D,K1], desc2 [D,K2] fp32
+ * (unit-norm columns, row-major like the reference's M x N arrays).  L2 distance sqrt(2 - 2*clip(d1.d2)), row and
+ * column argmin (ties -> lowest index, as np.argmin), keep i if score < nn_thresh and the match is mutual.
+ * Outputs (device): idx1/idx2/score [>= min(K1,K2)] in ascending idx1 order, *count = L.  nn_thresh < 0 is
+ * SPB_EINVAL (the reference raises ValueError); K1 == 0 or K2 == 0 gives count 0. */
+size_t spb_nn_match_workspace_bytes(int K1, int K2);
+int spb_nn_match_two_way(const float* desc1, int K1, const float* desc2, int K2, int D, float nn_thresh, int* idx1,
+                         int* idx2, float* score, int* count, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- (2) network ------------------------------------------------------------------------------------
  * models/SuperPointNet_pretrained.py:46-76, SuperPointNet_gauss2.py:43-70, SuperPointNet.py:154-224.
  * weights/biases: HOST pointers, 12 layers in the order conv1a,1b,2a,2b,3a,3b,4a,4b,Pa,Pb,Da,Db;

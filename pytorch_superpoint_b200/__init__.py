@@ -8,6 +8,6 @@ library; calling any operator does, and raises otherwise -- there is no CPU fall
 from .homographies import EXPORT_PARAMS, make_ha_homographies, sample_homography  # noqa: F401
 from .net import SuperPointNet_b200, fold_state_dict  # noqa: F401
 from .ops import (combine_heatmap, compute_valid_mask, flattenDetection, getPtsFromHeatmap,  # noqa: F401
-                  inv_warp_image_batch, sample_desc_from_points)
+                  inv_warp_image_batch, nn_match_two_way, sample_desc_from_points)
 
 __version__ = "0.1.0"

@@ -35,6 +35,8 @@ PROTOTYPES = {
     "spb_get_pts_from_heatmap": (_i, [_p, _i, _i, _i, _f, _i, _i, _i, _i, _p, _p, _p, _p, _z, _p]),
     "spb_sample_desc_from_points": (_i, [_p, _i, _p, _p, _i, _i, _i, _i, _i, _p, _p]),
     "spb_soft_argmax_points": (_i, [_p, _i, _i, _p, _p, _i, _i, _p, _p]),
+    "spb_nn_match_workspace_bytes": (_z, [_i, _i]),
+    "spb_nn_match_two_way": (_i, [_p, _i, _p, _i, _i, _f, _p, _p, _p, _p, _p, _z, _p]),
     "spb_net_create": (_i, [C.POINTER(_p), C.POINTER(_p), C.POINTER(_p)]),
     "spb_net_destroy": (_i, [_p]),
     "spb_net_set_impl": (_i, [_p, _i]),

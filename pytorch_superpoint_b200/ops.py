@@ -212,3 +212,34 @@ def sample_desc_from_points(coarse_desc, pts, cell=8):
         p = torch.cat([p, torch.zeros_like(p[:, :1])], dim=1)
     out = sample_desc_device(c[0], p.contiguous(), None, nhwc=False, cell=cell)
     return out.cpu().numpy().T.copy()
+
+
+def nn_match_two_way(desc1, desc2, nn_thresh):
+    """models/model_wrap.py:437-480 (PointTracker.nn_match_two_way): desc1 [D,K1], desc2 [D,K2] -> float64 [3,L]
+    rows (index in desc1, index in desc2, L2 distance), mutual nearest neighbours below ``nn_thresh``."""
+    d1 = np.asarray(desc1) if not torch.is_tensor(desc1) else desc1
+    d2 = np.asarray(desc2) if not torch.is_tensor(desc2) else desc2
+    assert d1.shape[0] == d2.shape[0]
+    if d1.shape[1] == 0 or d2.shape[1] == 0:
+        return np.zeros((3, 0))
+    if nn_thresh < 0.0:
+        raise ValueError("'nn_thresh' should be non-negative")
+    dev = _dev(d1.device if torch.is_tensor(d1) and d1.is_cuda else None)
+    a = torch.as_tensor(d1, dtype=torch.float32).to(dev).contiguous()
+    b = torch.as_tensor(d2, dtype=torch.float32).to(dev).contiguous()
+    D, K1, K2 = a.shape[0], a.shape[1], b.shape[1]
+    L = _lib.lib()
+    n = min(K1, K2)
+    idx1 = torch.empty(n, dtype=torch.int32, device=dev)
+    idx2 = torch.empty(n, dtype=torch.int32, device=dev)
+    score = torch.empty(n, dtype=torch.float32, device=dev)
+    count = torch.zeros(1, dtype=torch.int32, device=dev)
+    ws = torch.empty(int(L.spb_nn_match_workspace_bytes(K1, K2)), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(L.spb_nn_match_two_way(a.data_ptr(), K1, b.data_ptr(), K2, D, float(nn_thresh), idx1.data_ptr(),
+                                          idx2.data_ptr(), score.data_ptr(), count.data_ptr(), ws.data_ptr(), ws.numel(),
+                                          torch.cuda.current_stream().cuda_stream), "nn_match_two_way")
+    k = int(count.item())
+    out = np.zeros((3, k))
+    out[0], out[1], out[2] = idx1[:k].cpu().numpy(), idx2[:k].cpu().numpy(), score[:k].cpu().numpy()
+    return out

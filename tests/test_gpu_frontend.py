@@ -104,3 +104,49 @@ def test_export_entry_writes_reference_npz(tmp_path):
         assert np.all(np.diff(pts[:, 2]) <= 0)
     # resume: files exist -> nothing re-exported (export.py:302-306)
     assert export_detector_homoAdapt_b200(cfg, str(tmp_path), loader=samples, net=net) == 0
+
+
+def test_nn_match_two_way_vs_reference_golden(golden):
+    """PointTracker.nn_match_two_way on the GPU vs the matches of the reference on its own kitti_test artefact."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from pytorch_superpoint_b200.frontend import PointTracker_b200
+    g = golden("match")
+    tr = PointTracker_b200(nn_thresh=0.7)
+    m = tr.nn_match_two_way(g["desc1"].astype(np.float32), g["desc2"].astype(np.float32), 0.7)
+    assert m.dtype == np.float64 and np.array_equal(m[:2], g["matches"][:2])
+    np.testing.assert_allclose(m[2], g["matches"][2], atol=1e-6)
+    assert tr.get_mscores() is m
+
+
+@pytest.mark.parametrize("K1,K2,D,thr", [(1, 1, 256, 0.7), (37, 130, 256, 0.9), (513, 300, 256, 0.7), (1000, 1000, 256, 1.2),
+                                         (65, 64, 8, 2.1)])
+def test_nn_match_two_way_vs_oracle(K1, K2, D, thr):
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from pytorch_superpoint_b200 import nn_match_two_way
+    rng = np.random.RandomState(K1 + K2)
+    d1 = rng.randn(D, K1).astype(np.float32)
+    d2 = np.concatenate([d1[:, :min(K1, K2) // 2] + 0.3 * rng.randn(D, min(K1, K2) // 2).astype(np.float32),
+                         rng.randn(D, K2 - min(K1, K2) // 2).astype(np.float32)], axis=1)
+    d2 = d2[:, rng.permutation(K2)]
+    d1 /= np.linalg.norm(d1, axis=0, keepdims=True)
+    d2 /= np.linalg.norm(d2, axis=0, keepdims=True)
+    got, ref = nn_match_two_way(d1, d2, thr), O.nn_match_two_way(d1, d2, thr)
+    assert got.shape == ref.shape and np.array_equal(got[:2], ref[:2])
+    np.testing.assert_allclose(got[2], ref[2], atol=2e-6)
+
+
+def test_nn_match_two_way_edge_cases():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from pytorch_superpoint_b200 import nn_match_two_way
+    assert nn_match_two_way(np.zeros((256, 0), np.float32), np.ones((256, 5), np.float32), 0.7).shape == (3, 0)
+    assert nn_match_two_way(np.ones((256, 5), np.float32), np.zeros((256, 0), np.float32), 0.7).shape == (3, 0)
+    with pytest.raises(ValueError):
+        nn_match_two_way(np.ones((4, 2), np.float32), np.ones((4, 2), np.float32), -0.1)
+    # exact ties: identical columns -> np.argmin keeps the first index in both directions
+    d = np.zeros((4, 3), np.float32)
+    d[0] = 1.0
+    m = nn_match_two_way(d, d, 0.5)
+    assert np.array_equal(m, O.nn_match_two_way(d, d, 0.5))
