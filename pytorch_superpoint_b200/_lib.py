@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libspb200.so")
+LIB_PATH = os.environ.get("SPB200_LIB") or os.path.join(_HERE, "libspb200.so")  # SPB200_LIB: A/B builds of the kernels
 
 _p = C.c_void_p
 _i = C.c_int
@@ -52,7 +52,7 @@ PROTOTYPES = {
     "spb_ha_heatmap_sums_batch": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _i, _p, _z, _p]),
 }
 # debug knobs exported by the library but not part of the public header
-_EXTRA = {"spb_conv_tc_set_halo": (_i, [_i]), "spb_conv_tc_set_fuse1": (_i, [_i]), "spb_conv_tc_set_s3": (_i, [_i]),
+_EXTRA = {"spb_conv_tc_set_halo": (_i, [_i]), "spb_conv_tc_set_fuse1": (_i, [_i]), "spb_conv_tc_set_s3": (_i, [_i]), "spb_conv_tc_set_pair": (_i, [_i]),
           "spb_conv1_fused_set_probe": (_i, [_p])}
 
 IMPL_TCGEN05, IMPL_SIMT = 0, 1

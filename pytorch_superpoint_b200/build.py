@@ -12,6 +12,8 @@ SOURCES = ["warp.cu", "heat.cu", "nms.cu", "desc.cu", "match.cu", "conv_simt.cu"
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default", "--expt-relaxed-constexpr",
               "-Xptxas", "-v" if os.environ.get("SPB200_VERBOSE") else "-warn-spills"]
+if os.environ.get("SPB200_DEFINES"):  # e.g. "-DSPB_C1A_TAP=6" for A/B experiments
+    NVCC_FLAGS += os.environ["SPB200_DEFINES"].split()
 
 
 def _newer(a: str, b: str) -> bool:

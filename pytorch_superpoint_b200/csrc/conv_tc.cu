@@ -24,9 +24,11 @@ namespace spb {
 // ------------------------------------------------------------------------------------------------
 // OUT_: 0 = ReLU + bf16 NHWC (encoder / head 3x3), 1 = raw fp32 rows staged through shared memory for coalesced
 // stores (convPb: 65 channels), 2 = fp32 rows L2-normalised over the channels (convDb).
-template <int CIN_, int NPAD_, int KS_, bool HALO_, bool BRES_, int NA_, int NB_, bool POOL_, int OUT_>
+// NT_: output tiles per accumulator stage.  With streamed weights (128 -> 128) every weight block that arrives in shared
+// memory is used for TWO tiles (8 MMAs instead of 4): the layer was bound by L2 -> SM weight traffic (288 KB per tile).
+template <int CIN_, int NPAD_, int KS_, bool HALO_, bool BRES_, int NA_, int NB_, bool POOL_, int OUT_, int NT_ = 1>
 struct ConvCfg {
-  static constexpr int CIN = CIN_, NPAD = NPAD_, KS = KS_, NA = NA_, OUT = OUT_;
+  static constexpr int CIN = CIN_, NPAD = NPAD_, KS = KS_, NA = NA_, OUT = OUT_, NT = NT_;
   static constexpr bool POOL = POOL_;
   static constexpr int BW = (NPAD_ % 32 == 0) ? 32 : 16;  // TMEM columns per epilogue batch
   static constexpr int EPI_WARPS = OUT_ == 0 ? 8 : 4;     // bf16 layers: two warps per TMEM lane quadrant, half the columns each
@@ -47,8 +49,10 @@ struct ConvCfg {
   static constexpr int B_BYTES = NPAD * 128;
   static constexpr int NBLK = TAPS * CHUNKS;
   static constexpr int NBS = BRES ? NBLK : NB_;
-  static constexpr int ACC_STRIDE = NPAD <= 64 ? 64 : (NPAD <= 128 ? 128 : 256);
+  static constexpr int TILE_COLS = NPAD <= 64 ? 64 : (NPAD <= 128 ? 128 : 256);  // TMEM columns of one tile
+  static constexpr int ACC_STRIDE = NT * TILE_COLS;
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
+  static_assert(TMEM_COLS <= 512 && (NT == 1 || (HALO_ && KS_ > 1 && OUT_ == 0 && NPAD_ >= 128)), "tile pairs: halo + TMA-store layers");
   static constexpr int NBAR = 2 * NA + 2 * NBS + 4 + 2;  // + the two issue tokens
   static constexpr size_t SMEM = 1024 /*align slack*/ + (size_t)NA * A_STRIDE + (size_t)NBS * B_BYTES + OSTAGE_BYTES +
                                  NPAD * 4 + NBAR * 8 + 16 + STAGE_BYTES;
@@ -60,7 +64,8 @@ struct ConvArgs {
   const float* bias;
   void* out;
   int B, H, W, cout;
-  int tiles_x, tiles_y, ntiles;
+  int tiles_x, tiles_y, ntiles;  // ntiles = real tiles; super-tile s covers tiles s*NT .. s*NT+NT-1 (missing ones are
+  int nst;                       // dummies in image B: TMA zero-fills their loads and clips their stores)
 };
 
 template <class C>
@@ -121,16 +126,22 @@ __global__ void __launch_bounds__(C::THREADS, 1) conv_tc_kernel(const __grid_con
     if (lane == 0) {
       int sa = 0, pa = 0, sb = 0, pb = 0;
       bool first = true;
-      for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x) {
-        const int n = t / (a.tiles_x * a.tiles_y), rem = t % (a.tiles_x * a.tiles_y);
+      const int tpv = a.tiles_x * a.tiles_y;
+      for (int st = blockIdx.x; st < a.nst; st += gridDim.x) {
+        const int t = st * C::NT;  // (NT == 1: the tile itself)
+        const int n = t / tpv, rem = t % tpv;
         const int y0 = (rem / a.tiles_x) * C::TH, x0 = (rem % a.tiles_x) * C::TW;
         for (int kc = 0; kc < C::CHUNKS; ++kc) {
           if (C::HALO) {
-            mbar_wait(a_empty(sa), pa ^ 1);
-            mbar_expect_tx(a_full(sa), C::A_BYTES);
-            tma_load_4d(smem_u32(sA + (size_t)sa * C::A_STRIDE), &tm_act, a_full(sa), kc * 64, x0 - C::KS / 2,
-                        y0 - C::KS / 2, n);
-            if (++sa == C::NA) { sa = 0; pa ^= 1; }
+#pragma unroll
+            for (int u = 0; u < C::NT; ++u) {
+              const int tu = t + u, nu = tu < a.ntiles ? tu / tpv : a.B, ru = tu < a.ntiles ? tu % tpv : 0;
+              mbar_wait(a_empty(sa), pa ^ 1);
+              mbar_expect_tx(a_full(sa), C::A_BYTES);
+              tma_load_4d(smem_u32(sA + (size_t)sa * C::A_STRIDE), &tm_act, a_full(sa), kc * 64,
+                          (ru % a.tiles_x) * C::TW - C::KS / 2, (ru / a.tiles_x) * C::TH - C::KS / 2, nu);
+              if (++sa == C::NA) { sa = 0; pa ^= 1; }
+            }
           }
           for (int tap = 0; tap < C::TAPS; ++tap) {
             if (!C::HALO) {
@@ -171,7 +182,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) conv_tc_kernel(const __grid_con
     constexpr uint32_t idesc = make_idesc(128, C::NPAD);
     constexpr uint64_t desc_hi_a = ((uint64_t)((C::P * 128) >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
     constexpr uint64_t desc_hi_b = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
-    constexpr int A_PER_TILE = C::HALO ? C::CHUNKS : C::CHUNKS * C::TAPS;
+    constexpr int A_PER_TILE = (C::HALO ? C::CHUNKS : C::CHUNKS * C::TAPS) * C::NT;  // A stages per super-tile
     // the token is handed over after this (chunk, tap) group has been issued
     constexpr int PASS_KC = C::TAPS >= 3 ? C::CHUNKS - 1 : C::CHUNKS - 2;
     constexpr int PASS_TAP = C::TAPS >= 3 ? C::TAPS - 3 : 0;
@@ -188,7 +199,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) conv_tc_kernel(const __grid_con
     }
     const uint32_t d_tmem = tmem_base + (uint32_t)q * C::ACC_STRIDE;
     int k = 0;  // this issuer's tile counter
-    for (int t = blockIdx.x + q * gridDim.x; t < a.ntiles; t += 2 * gridDim.x, ++k) {
+    for (int t = blockIdx.x + q * gridDim.x; t < a.nst; t += 2 * gridDim.x, ++k) {
       const bool first = k == 0;
       mbar_wait(acc_empty(q), (k & 1) ^ 1);
       mbar_wait(a_full(sa), pa);  // first operand block of the tile (waited again, for free, in the loop)
@@ -196,7 +207,16 @@ __global__ void __launch_bounds__(C::THREADS, 1) conv_tc_kernel(const __grid_con
       tc_fence_after();
 #pragma unroll 1
       for (int kc = 0; kc < C::CHUNKS; ++kc) {
-        if (C::HALO) mbar_wait(a_full(sa), pa);
+        int sau[C::NT];  // the A stages of this chunk, one per tile of the super-tile
+        if (C::HALO) {
+          int s2 = sa, p2 = pa;
+#pragma unroll
+          for (int u = 0; u < C::NT; ++u) {
+            mbar_wait(a_full(s2), p2);
+            sau[u] = s2;
+            if (++s2 == C::NA) { s2 = 0; p2 ^= 1; }
+          }
+        }
 #pragma unroll
         for (int tap = 0; tap < C::TAPS; ++tap) {
           if (!C::HALO) mbar_wait(a_full(sa), pa);
@@ -208,16 +228,24 @@ __global__ void __launch_bounds__(C::THREADS, 1) conv_tc_kernel(const __grid_con
           }
           tc_fence_after();
           const uint32_t tap_off = C::HALO ? ((tap / C::KS) * C::P + (tap % C::KS)) * 128 : 0;
-          const uint64_t adesc = desc_hi_a | (uint64_t)(((sA_u32 + (uint32_t)sa * C::A_STRIDE + tap_off) >> 4) | (1u << 16));
           const uint64_t bdesc = desc_hi_b | (uint64_t)(((sB_u32 + (uint32_t)slot * C::B_BYTES) >> 4) | (1u << 16));
           if (elect_one()) {
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk)
-              tc_mma(d_tmem, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc,
-                     (kc | tap | kk) != 0 ? 1u : 0u);
+            for (int u = 0; u < C::NT; ++u) {
+              const int su = C::HALO ? sau[u] : sa;
+              const uint64_t adesc =
+                  desc_hi_a | (uint64_t)(((sA_u32 + (uint32_t)su * C::A_STRIDE + tap_off) >> 4) | (1u << 16));
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk)
+                tc_mma(d_tmem + u * C::TILE_COLS, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc,
+                       (kc | tap | kk) != 0 ? 1u : 0u);
+            }
             if (!C::BRES) tc_commit(b_empty(sb));
             if (!C::HALO) tc_commit(a_empty(sa));
-            if (C::HALO && tap == C::TAPS - 1) tc_commit(a_empty(sa));
+            if (C::HALO && tap == C::TAPS - 1) {
+#pragma unroll
+              for (int u = 0; u < C::NT; ++u) tc_commit(a_empty(sau[u]));
+            }
             if (kc == C::CHUNKS - 1 && tap == C::TAPS - 1) tc_commit(acc_full(q));
             if (kc == PASS_KC && tap == PASS_TAP) mbar_arrive(token(q ^ 1));
           }
@@ -229,9 +257,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) conv_tc_kernel(const __grid_con
             if (++sa == C::NA) { sa = 0; pa ^= 1; }
           }
         }
-        if (C::HALO) {
-          if (++sa == C::NA) { sa = 0; pa ^= 1; }
-        }
+        if (C::HALO) advance(sa, pa, C::NT, C::NA);
       }
       // skip the other issuer's tile in both rings
       advance(sa, pa, A_PER_TILE, C::NA);
@@ -248,13 +274,18 @@ __global__ void __launch_bounds__(C::THREADS, 1) conv_tc_kernel(const __grid_con
     constexpr int BW = C::BW, NBATCH = COLS / BW;
     const int col0 = ((warp - 2) >> 2) * COLS;
     int as = 0, pacc = 0;
-    for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x) {
-      const int n = t / (a.tiles_x * a.tiles_y), rem = t % (a.tiles_x * a.tiles_y);
-      const int y0 = (rem / a.tiles_x) * C::TH, x0 = (rem % a.tiles_x) * C::TW;
-      const int y = y0 + py, x = x0 + px;
+    const int tpv = a.tiles_x * a.tiles_y;
+    for (int sti = blockIdx.x; sti < a.nst; sti += gridDim.x) {
       mbar_wait(acc_full(as), pacc);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (uint32_t)as * C::ACC_STRIDE + ((uint32_t)(quad * 32) << 16);
+#pragma unroll 1
+     for (int u = 0; u < C::NT; ++u) {  // the tiles of this accumulator stage
+      const int t = sti * C::NT + u;
+      const int n = t < a.ntiles ? t / tpv : a.B, rem = t < a.ntiles ? t % tpv : 0;  // dummy tile: image B (clipped)
+      const int y0 = (rem / a.tiles_x) * C::TH, x0 = (rem % a.tiles_x) * C::TW;
+      const int y = y0 + py, x = x0 + px;
+      const uint32_t taddr =
+          tmem_base + (uint32_t)as * C::ACC_STRIDE + (uint32_t)u * C::TILE_COLS + ((uint32_t)(quad * 32) << 16);
       bool valid = y < a.H && x < a.W;
       long long opix;
       if (C::POOL) {
@@ -310,8 +341,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) conv_tc_kernel(const __grid_con
                 make_float4(__fdiv_rn(__uint_as_float(w[j]), sum), __fdiv_rn(__uint_as_float(w[j + 1]), sum),
                             __fdiv_rn(__uint_as_float(w[j + 2]), sum), __fdiv_rn(__uint_as_float(w[j + 3]), sum));
         }
-        if (++as == 2) { as = 0; pacc ^= 1; }
-        continue;
+        continue;  // (NT == 1: falls out of the tile loop to the stage advance below)
       }
       uint32_t v[2][BW];
       tc_ld_nowait<BW>(taddr + col0, v[0]);
@@ -320,7 +350,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) conv_tc_kernel(const __grid_con
         tc_wait_ld();
         if (b + 1 < NBATCH) {
           tc_ld_nowait<BW>(taddr + col0 + (b + 1) * BW, v[(b + 1) & 1]);
-        } else {
+        } else if (u == C::NT - 1) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(acc_empty(as));
@@ -422,6 +452,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) conv_tc_kernel(const __grid_con
         }
         __syncwarp();
       }
+     }  // tiles of the stage
       if (++as == 2) { as = 0; pacc ^= 1; }
     }
     if (C::TMA_OUT && lane == 0) tma_store_wait_read<0>();
@@ -608,6 +639,9 @@ struct Conv1FusedSmem {
   uint32_t tmem_slot;
 };
 
+#ifndef SPB_C1A_TAP
+#define SPB_C1A_TAP 8  // conv1a of the issuer's next tile is issued behind this tap of conv1b
+#endif
 struct Conv1FusedArgs {
   const __nv_bfloat16* w1a;     // [64][16]
   const float *bias1, *bias2;
@@ -734,11 +768,9 @@ __global__ void __launch_bounds__(576, 1) conv1_fused_kernel(const __grid_consta
           }
         }
         __syncwarp();
+        if (tap == SPB_C1A_TAP && t + 2 * (int)gridDim.x < a.ntiles) issue_conv1a(k + 1);
       }
       SPB_PROBE(4);
-      // (issuing conv1a(k+1) in the MIDDLE of conv1b instead was measured 3x slower: the issuer then stalls with
-      // the token in hand whenever stage 1 is not ahead, and both issuers end up waiting on each other)
-      if (t + 2 * (int)gridDim.x < a.ntiles) issue_conv1a(k + 1);
     }
   } else if (warp >= 10) {
     // =========================== stage 1: im2col build + conv1a epilogue into conv1b's A operand =========
@@ -1075,6 +1107,11 @@ int conv_tc_prepare(LayerDev& L) {
   return SPB_OK;
 }
 
+static int g_pair = 1;  // 128 -> 128 layers: two tiles per accumulator stage / weight pass (0: one, for A/B tests)
+extern "C" int spb_conv_tc_set_pair(int on) {
+  g_pair = on ? 1 : 0;
+  return SPB_OK;
+}
 static int g_halo_mode = 1;  // 1: one halo block + shifted descriptors; 0: per-tap reload (debug/A-B)
 extern "C" int spb_conv_tc_set_halo(int on) {
   g_halo_mode = on ? 1 : 0;
@@ -1111,8 +1148,9 @@ static int launch(const LayerDev& L, const __nv_bfloat16* in, void* out, int B, 
   a.tiles_x = ceil_div(W, C::TW);
   a.tiles_y = ceil_div(H, C::TH);
   a.ntiles = B * a.tiles_x * a.tiles_y;
+  a.nst = (a.ntiles + C::NT - 1) / C::NT;
   SPB_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
-  const int grid = a.ntiles < kNumSMs ? a.ntiles : kNumSMs;
+  const int grid = a.nst < kNumSMs ? a.nst : kNumSMs;
   conv_tc_kernel<C><<<grid, C::THREADS, C::SMEM, st>>>(tm_act, tm_wgt, tm_out, a);
   SPB_CHECK_LAUNCH();
   return SPB_OK;
@@ -1133,6 +1171,8 @@ int conv_tc(const LayerDev& L, const __nv_bfloat16* in, void* out, int B, int H,
   const bool halo = g_halo_mode != 0;
 #define SPB_CONV(CIN, NPAD, KS, HALO, BRES, NA, NB, POOL, OUT) \
   launch<ConvCfg<CIN, NPAD, KS, HALO, BRES, NA, NB, POOL, OUT>>(L, in, out, B, H, W, out_mode, st)
+#define SPB_CONV2(CIN, NPAD, KS, HALO, BRES, NA, NB, POOL, OUT) \
+  launch<ConvCfg<CIN, NPAD, KS, HALO, BRES, NA, NB, POOL, OUT, 2>>(L, in, out, B, H, W, out_mode, st)
   if (L.ks == 3 && L.cin == 64 && L.cout_pad == 64) {
     if (L.pool) return halo ? SPB_CONV(64, 64, 3, true, true, 4, 0, true, 0) : SPB_CONV(64, 64, 3, false, true, 6, 0, true, 0);
     return halo ? SPB_CONV(64, 64, 3, true, true, 4, 0, false, 0) : SPB_CONV(64, 64, 3, false, true, 6, 0, false, 0);
@@ -1140,6 +1180,8 @@ int conv_tc(const LayerDev& L, const __nv_bfloat16* in, void* out, int B, int H,
   if (L.ks == 3 && L.cin == 64 && L.cout_pad == 128)
     return halo ? SPB_CONV(64, 128, 3, true, true, 2, 0, false, 0) : SPB_CONV(64, 128, 3, false, true, 3, 0, false, 0);
   if (L.ks == 3 && L.cin == 128 && L.cout_pad == 128) {
+    // tile pairs: every streamed weight block feeds two tiles (g_pair == 0: one tile per stage, for A/B tests)
+    if (halo && g_pair) return L.pool ? SPB_CONV2(128, 128, 3, true, false, 4, 6, true, 0) : SPB_CONV2(128, 128, 3, true, false, 4, 6, false, 0);
     if (L.pool) return halo ? SPB_CONV(128, 128, 3, true, false, 4, 6, true, 0) : SPB_CONV(128, 128, 3, false, false, 6, 6, true, 0);
     return halo ? SPB_CONV(128, 128, 3, true, false, 4, 6, false, 0) : SPB_CONV(128, 128, 3, false, false, 6, 6, false, 0);
   }
@@ -1149,6 +1191,7 @@ int conv_tc(const LayerDev& L, const __nv_bfloat16* in, void* out, int B, int H,
   if (L.ks == 1 && L.cin == 256 && L.cout_pad == 80 && out_mode == 3) return SPB_CONV(256, 80, 1, false, true, 6, 0, false, 3);
   if (L.ks == 1 && L.cin == 256 && L.cout_pad == 256 && out_mode == 2) return SPB_CONV(256, 256, 1, false, true, 4, 0, false, 2);
 #undef SPB_CONV
+#undef SPB_CONV2
   set_error("conv_tc: unsupported layer shape ks=%d cin=%d cout_pad=%d", L.ks, L.cin, L.cout_pad);
   return SPB_EINVAL;
 }

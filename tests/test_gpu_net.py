@@ -104,6 +104,25 @@ def test_s3_column_stacked_kernel(net, li, B, H, W):
     assert (s3 != win).float().mean().item() < 0.02  # same products, different fp32 summation order: rare 1-ulp flips
 
 
+@pytest.mark.parametrize("li,B,H,W", [(5, 3, 60, 80), (5, 1, 16, 8), (6, 5, 30, 40), (7, 7, 30, 40), (6, 1, 16, 8),
+                                      (5, 2, 34, 50)])
+def test_tile_pairs_equal_single_tiles(net, li, B, H, W):
+    """128->128 layers: two tiles per accumulator stage / weight pass (odd tile counts end in a dummy tile that TMA
+    zero-fills and clips) == one tile per stage, bit for bit (same per-tile accumulation order)."""
+    from pytorch_superpoint_b200 import _lib
+    L = _lib.lib()
+    torch.manual_seed(li + H)
+    x = (torch.randn(B, H, W, 128, device="cuda") * 0.5).to(torch.bfloat16).contiguous()
+    try:
+        L.spb_conv_tc_set_pair(0)
+        one = _layer(net, li, x, B, H, W, "tcgen05")
+        L.spb_conv_tc_set_pair(1)
+        two = _layer(net, li, x, B, H, W, "tcgen05")
+    finally:
+        L.spb_conv_tc_set_pair(1)
+    assert torch.isfinite(two.float()).all() and torch.equal(one, two)
+
+
 @pytest.mark.parametrize("B,H,W", [(1, 16, 8), (3, 24, 40), (2, 240, 320), (5, 30, 52)])
 def test_conv1a_tensor_core_vs_simt(net, B, H, W):
     """conv1a as a K=16 im2col MMA: same bf16 numerics as the CUDA-core kernel, incl. ragged last tile."""
