@@ -23,17 +23,21 @@
 //     quadrant for ox < 14, and both partners of the 2x2 max-pool (lane^1, lane^16) are in the same warp;
 //   * weights [r][(s, co)][ci] stay resident in shared memory (72 KB), accumulators double buffered in TMEM
 //     (2 x 192 columns), two MMA issuer warps alternate tiles with a token hand-over (see conv_tc.cu).
-// Warps: 0 TMA producer, 1 and 10 MMA issuers, 2..9 epilogue (two per TMEM quadrant, 32 channels each).
+// Warps: 0 TMA producer, 1 and 18 MMA issuers, 2..17 epilogue in two groups of 8 that alternate tiles.
 #include "tc_common.cuh"
 
 namespace spb {
 
-constexpr int kS3Rows = 8, kS3Cols = 14, kS3Win = 16, kS3NA = 4;
+#ifndef SPB_S3_NA
+#define SPB_S3_NA 4
+#endif
+constexpr int kS3Rows = 8, kS3Cols = 14, kS3Win = 16, kS3NA = SPB_S3_NA;
 
 struct S3Smem {
   uint8_t b[3][24576];         // per tap row: 192 rows (s, co) x 128 B, SWIZZLE_128B
   uint8_t a[kS3NA][20480];     // 10 rows x 16 pixels x 128 B, SWIZZLE_128B
-  uint8_t stage[2][14336];     // output tile 8 x 14 pixels x 128 B (pooled: 4 x 7), SWIZZLE_128B, TMA store source
+  uint8_t stage[2][2][14336];  // [epilogue group][buffer]: output tile 8 x 14 pixels x 128 B (pooled: 4 x 7),
+                               // SWIZZLE_128B, TMA store source
   float bias[64];
   uint64_t bars[3 + 2 * kS3NA + 6];  // b_full[3], a_full[NA], a_empty[NA], acc_full[2], acc_empty[2], token[2]
   uint32_t tmem_slot;
@@ -69,8 +73,13 @@ __device__ __forceinline__ void s3_pack16(const float (&f)[16], uint32_t* pk) {
   }
 }
 
+#ifndef SPB_S3_TOKEN_R
+#define SPB_S3_TOKEN_R 0  // the issue token is handed over behind this tap row (0, 1 and 2 measure the same)
+#endif
+constexpr int kS3EpiWarps = 16, kS3Threads = 64 + 32 * kS3EpiWarps + 32;
+
 template <bool POOL>
-__global__ void __launch_bounds__(352, 1) conv_s3_kernel(const __grid_constant__ CUtensorMap tm_act,
+__global__ void __launch_bounds__(kS3Threads, 1) conv_s3_kernel(const __grid_constant__ CUtensorMap tm_act,
                                                          const __grid_constant__ CUtensorMap tm_wgt,
                                                          const __grid_constant__ CUtensorMap tm_out, S3Args a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -93,7 +102,7 @@ __global__ void __launch_bounds__(352, 1) conv_s3_kernel(const __grid_constant__
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(acc_full(s), 1);
-      mbar_init(acc_empty(s), 8);
+      mbar_init(acc_empty(s), kS3EpiWarps / 2);
       mbar_init(token(s), 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -122,13 +131,13 @@ __global__ void __launch_bounds__(352, 1) conv_s3_kernel(const __grid_constant__
       for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x, ++it) {
         const int n = t / tiles_per_view, rem = t % tiles_per_view;
         const int y0 = (rem / a.tiles_x) * kS3Rows, x0 = (rem % a.tiles_x) * kS3Cols;
-        const int sa = it & (kS3NA - 1), pa = (it / kS3NA) & 1;
+        const int sa = it % kS3NA, pa = (it / kS3NA) & 1;
         mbar_wait(a_empty(sa), pa ^ 1);
         mbar_expect_tx(a_full(sa), 20480);
         tma_load_4d(smem_u32(sm.a[sa]), &tm_act, a_full(sa), 0, x0 - 1, y0 - 1, n);
       }
     }
-  } else if (warp == 1 || warp == 10) {
+  } else if (warp == 1 || warp == 2 + kS3EpiWarps) {
     // =========================== MMA issuers (alternate tiles, token hand-over after tap row 0) ===========
     const int q = warp == 1 ? 0 : 1;
     constexpr uint32_t idesc = make_idesc(128, 192);
@@ -137,7 +146,7 @@ __global__ void __launch_bounds__(352, 1) conv_s3_kernel(const __grid_constant__
     int k = 0;
     for (int t = blockIdx.x + q * gridDim.x; t < a.ntiles; t += 2 * gridDim.x, ++k) {
       const int it = 2 * k + q;
-      const int sa = it & (kS3NA - 1), pa = (it / kS3NA) & 1;
+      const int sa = it % kS3NA, pa = (it / kS3NA) & 1;
       mbar_wait(acc_empty(q), (k & 1) ^ 1);
       mbar_wait(a_full(sa), pa);
       if (q == 1 || k > 0) mbar_wait(token(q), (q == 0 ? k - 1 : k) & 1);
@@ -155,7 +164,7 @@ __global__ void __launch_bounds__(352, 1) conv_s3_kernel(const __grid_constant__
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
             tc_mma(d_tmem, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, (r | kk) != 0 ? 1u : 0u);
-          if (r == 0) mbar_arrive(token(q ^ 1));
+          if (r == SPB_S3_TOKEN_R) mbar_arrive(token(q ^ 1));
           if (r == 2) {
             tc_commit(a_empty(sa));
             tc_commit(acc_full(q));
@@ -165,68 +174,77 @@ __global__ void __launch_bounds__(352, 1) conv_s3_kernel(const __grid_constant__
       }
     }
   } else {
-    // =========================== epilogue (warps 2..9) ===========================
-    const int quad = warp & 3, chalf = (warp - 2) >> 2;
+    // =========================== epilogue (warps 2..17): two groups of 8 warps alternate tiles ===========
+    // One warp's chain per tile (barrier wait -> tcgen05.ld -> shuffle-add -> pack -> pool -> stage -> fence ->
+    // named barrier -> TMA store) is ~1400 cycles of latency against 1152 MMA cycles per tile, so a single group
+    // processing every tile in lock-step was what the tensor pipe waited for (measured: the kernel WITHOUT its
+    // MMAs ran at 70 % of the full kernel's time).  Group g owns the tiles of parity g = accumulator stage g, two
+    // staging buffers of its own and named barrier 1+g; each warp converts 32 channels of its TMEM quadrant.
+    const int grp = (warp - 2) >> 3, quad = warp & 3, chalf = ((warp - 2) >> 2) & 1;
     const int ry = 2 * quad + (lane >> 4), ox = lane & 15;  // tile row / window column of this thread's TMEM lane
-    float bz[32];  // this warp's 32 channel biases stay in registers (an LDS is a shared-memory wavefront too)
-#pragma unroll
-    for (int j = 0; j < 32; ++j) bz[j] = sm.bias[chalf * 32 + j];
-    int it = 0;
-    for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x, ++it) {
-      const int as = it & 1, pacc = (it >> 1) & 1;
+    const bool store_thread = threadIdx.x == 64 + grp * 256;
+    // row of the staging tile this thread owns (the TMA store clips what lies outside the image)
+    const bool owner = ox < kS3Cols && (!POOL || !(lane & 17));  // pooled: even column, even row of the window
+    const int p = POOL ? (ry >> 1) * (kS3Cols / 2) + (ox >> 1) : ry * kS3Cols + ox;
+    const float* bz = sm.bias + chalf * 32;  // (registers are the scarcer resource at 608 threads: 4 LDS.128 per batch)
+    int k = 0;  // this group's tile counter
+    for (int t = blockIdx.x + grp * gridDim.x; t < a.ntiles; t += 2 * gridDim.x, ++k) {
       const int n = t / tiles_per_view, rem = t % tiles_per_view;
       const int y0 = (rem / a.tiles_x) * kS3Rows, x0 = (rem % a.tiles_x) * kS3Cols;
-      // row of the staging tile this thread owns (the TMA store clips what lies outside the image)
-      const bool owner = ox < kS3Cols && (!POOL || !(lane & 17));  // pooled: even column, even row of the window
-      const int p = POOL ? (ry >> 1) * (kS3Cols / 2) + (ox >> 1) : ry * kS3Cols + ox;
-      mbar_wait(acc_full(as), pacc);
+      mbar_wait(acc_full(grp), k & 1);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (uint32_t)as * 192 + chalf * 32 + ((uint32_t)(quad * 32) << 16);
-      uint32_t c[2][3][16];
-#pragma unroll
-      for (int cb = 0; cb < 2; ++cb)
-#pragma unroll
-        for (int s = 0; s < 3; ++s) tc_ld_nowait<16>(taddr + s * 64 + cb * 16, c[cb][s]);
-      tc_wait_ld();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(acc_empty(as));
+      const uint32_t taddr = tmem_base + (uint32_t)grp * 192 + chalf * 32 + ((uint32_t)(quad * 32) << 16);
       uint32_t pk[16];
 #pragma unroll
-      for (int cb = 0; cb < 2; ++cb) {
+      for (int cb = 0; cb < 2; ++cb) {  // two batches of 16 channels (48 live accumulator registers at a time)
+        uint32_t c[3][16];
+#pragma unroll
+        for (int s = 0; s < 3; ++s) tc_ld_nowait<16>(taddr + s * 64 + cb * 16, c[s]);
+        tc_wait_ld();
+        if (cb == 1) {  // everything this warp needs has left the accumulator
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(acc_empty(grp));
+        }
         float f[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float c1 = __shfl_down_sync(0xffffffffu, __uint_as_float(c[cb][1][j]), 1);
-          const float c2 = __shfl_down_sync(0xffffffffu, __uint_as_float(c[cb][2][j]), 2);
-          f[j] = ((__uint_as_float(c[cb][0][j]) + c1) + c2) + bz[cb * 16 + j];
+        for (int j = 0; j < 16; j += 4) {
+          const float4 bb = *reinterpret_cast<const float4*>(bz + cb * 16 + j);
+          const float bj[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float c1 = __shfl_down_sync(0xffffffffu, __uint_as_float(c[1][j + e]), 1);
+            const float c2 = __shfl_down_sync(0xffffffffu, __uint_as_float(c[2][j + e]), 2);
+            f[j + e] = ((__uint_as_float(c[0][j + e]) + c1) + c2) + bj[e];
+          }
         }
         s3_pack16<POOL>(f, pk + cb * 8);
       }
       // Stage the tile in shared memory (SWIZZLE_128B rows = pixels) and let ONE TMA tensor store write it:
       // per-lane 16-byte global stores at a 128-byte stride cost one L1 wavefront per lane and competed with the
       // tensor core's operand reads for the shared-memory pipe (78 % L1/TEX busy, ncu r01).
+      uint8_t* stg = sm.stage[grp][k & 1];
       if (owner) {
-        uint8_t* srow = sm.stage[as] + p * 128;
+        uint8_t* srow = stg + p * 128;
 #pragma unroll
         for (int v = 0; v < 4; ++v)
           *reinterpret_cast<uint4*>(srow + (((chalf * 4 + v) ^ (p & 7)) * 16)) =
               make_uint4(pk[4 * v], pk[4 * v + 1], pk[4 * v + 2], pk[4 * v + 3]);
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      // the store issued two tiles ago (the other staging buffer's previous use) must have drained before anyone
-      // passes this barrier and starts writing that buffer for the next tile
-      if (threadIdx.x == 64) tma_store_wait_read<0>();
-      named_bar_sync(1, 256);
-      if (threadIdx.x == 64) {
+      // the group's previous store (its other staging buffer) must have drained before anyone passes this
+      // barrier and starts writing that buffer for the group's next tile
+      if (store_thread) tma_store_wait_read<0>();
+      named_bar_sync(1 + grp, 256);
+      if (store_thread) {
         if (POOL)
-          tma_store_4d(&tm_out, smem_u32(sm.stage[as]), 0, x0 >> 1, y0 >> 1, n);
+          tma_store_4d(&tm_out, smem_u32(stg), 0, x0 >> 1, y0 >> 1, n);
         else
-          tma_store_4d(&tm_out, smem_u32(sm.stage[as]), 0, x0, y0, n);
+          tma_store_4d(&tm_out, smem_u32(stg), 0, x0, y0, n);
         tma_store_commit();
       }
     }
-    if (threadIdx.x == 64) tma_store_wait_read<0>();
+    if (store_thread) tma_store_wait_read<0>();
   }
   tc_fence_before();
   __syncthreads();
@@ -293,7 +311,7 @@ static int launch_s3(const LayerDev& L, const __nv_bfloat16* in, __nv_bfloat16* 
   const int smem = (int)sizeof(S3Smem) + 1024;
   SPB_CHECK_CUDA(cudaFuncSetAttribute(conv_s3_kernel<POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int grid = a.ntiles < kNumSMs ? a.ntiles : kNumSMs;
-  conv_s3_kernel<POOL><<<grid, 352, smem, st>>>(tm_act, tm_wgt, tm_out, a);
+  conv_s3_kernel<POOL><<<grid, kS3Threads, smem, st>>>(tm_act, tm_wgt, tm_out, a);
   SPB_CHECK_LAUNCH();
   return SPB_OK;
 }
