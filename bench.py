@@ -39,7 +39,9 @@ UNIT = "images/s"
 WORKLOAD = ("HA export: 100 homographies x 240x320 (configs[1], magicpoint_coco_export.yaml shape); "
             "SuperPointNet_gauss2 weights, seeded random init, eval-mode BN folded; thr 0.015, nms 4, top_k 600")
 CONV_GFLOP_DET = 12.161  # conv FLOPs per 240x320 view, detector path only
-TRAFFIC_BYTES_PER_VIEW = None  # filled from profiles/r01_ncu_conv1_fused.txt (dram read+write per view)
+# dram__bytes_read.sum + dram__bytes_write.sum of conv1_fused_kernel per view: 0.2461 GB + 1.9083 GB over one 800-view
+# launch (ncu --set full, profiles/r01_ncu_top_kernels.txt); algorithmic = 0.307 MB fp32 in + 2.458 MB pooled bf16 out
+TRAFFIC_BYTES_PER_VIEW = (0.246116e9 + 1.908269e9) / 800
 
 
 def structured_images(n, seed=0):
@@ -87,7 +89,18 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.monotonic(), [c.strip() for c in line.split(",")]))
+
+    def window(self, t0, t1):
+        """Keep the samples taken inside [t0, t1] (the timed region); nvidia-smi needs ~100 ms to start, so the
+        sampler is started before the warm-up steps.  If the region was shorter than one sampling period, keep the
+        samples closest to it (taken under the same load: the warm-up steps run the same kernels)."""
+        time.sleep(0.06)
+        inside = [r for ts, r in self.rows if t0 <= ts <= t1 + 0.05]
+        if not inside and self.rows:
+            near = sorted(self.rows, key=lambda tr: min(abs(tr[0] - t0), abs(tr[0] - t1)))[:2]
+            inside = [r for _, r in near]
+        self.rows = [(0.0, r) for r in inside]
 
     def __exit__(self, *a):
         if self.proc:
@@ -98,10 +111,11 @@ class ClockSampler:
                 self.proc.kill()
 
     def summary(self):
-        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        rows = [r for _, r in self.rows]
+        sm = [float(r[0]) for r in rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for j, n in enumerate(names) if any(len(r) >= 6 and r[2 + j].startswith("Active") for r in self.rows)]
+        reasons = [n for j, n in enumerate(names) if any(len(r) >= 6 and r[2 + j].startswith("Active") for r in rows)]
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": reasons, "samples": len(sm)}
 
@@ -200,11 +214,13 @@ def run_b200(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    for _ in range(max(args.warmup, 3)):
-        step_resident()
-    launches0 = L.spb_launch_count()
     with ClockSampler(local) as clk:
+        for _ in range(max(args.warmup, 3)):
+            step_resident()
+        launches0 = L.spb_launch_count()
+        t_region0 = time.monotonic()
         ms = timed(step_resident, args.steps)
+        clk.window(t_region0, time.monotonic())
     launches = int(L.spb_launch_count() - launches0)
     value = B * args.steps / (ms / 1e3)
 

@@ -38,7 +38,9 @@ struct ConvCfg {
   // write it with one TMA tensor store: per-lane 16-byte global stores at a 256/512-byte stride cost one L1
   // wavefront per lane, in the shared-memory pipe the tensor core reads its operands through
   static constexpr bool TMA_OUT = OUT_ == 0 && NPAD_ >= 128;
-  static constexpr int OSTAGE_BYTES = TMA_OUT ? 8 * 4096 : 0;
+  // OUT_ == 3 (softmax probabilities, fp32 [.,64]): each of the 4 epilogue warps stages 32 pixels x 2 halves of
+  // 32 floats (2 x 4 KB, SWIZZLE_128B) and issues two TMA stores
+  static constexpr int OSTAGE_BYTES = TMA_OUT ? 8 * 4096 : (OUT_ == 3 ? 4 * 8192 : 0);
   static constexpr bool HALO = HALO_ && KS_ > 1, BRES = BRES_;
   static constexpr int TAPS = KS * KS, CHUNKS = CIN / 64;
   static constexpr int TH = 16, TW = 8;
@@ -326,20 +328,36 @@ __global__ void __launch_bounds__(C::THREADS, 1) conv_tc_kernel(const __grid_con
           w[j] = __float_as_uint(f);
           mx = fmaxf(mx, f);
         }
+        // The logits come from bf16 tensor-core products (parity is a 1e-2 tolerance on the heat-map, not bit-exact),
+        // so the softmax uses the fast exponential and ONE reciprocal per cell: the IEEE expf/div sequences were
+        // ~1800 instructions per thread and made this epilogue the layer's critical path.
         float sum = 0.f;
 #pragma unroll
         for (int j = 0; j < 65; ++j) {
-          const float e = expf(__uint_as_float(w[j]) - mx);
+          const float e = __expf(__uint_as_float(w[j]) - mx);
           w[j] = __float_as_uint(e);
           sum += e;
         }
-        if (valid) {
-          float* o = static_cast<float*>(a.out) + opix * 64;
+        const float rs = __frcp_rn(sum);
+        // stage [pixel][32 floats] x 2 halves (SWIZZLE_128B) and let TMA write the warp's 4 rows x 8 pixels
+        uint8_t* stg = sOut + (warp - 2) * 8192;
+        if (lane == 0) tma_store_wait_read<0>();  // the previous tile's stores have finished reading the tile
+        __syncwarp();
 #pragma unroll
-          for (int j = 0; j < 64; j += 4)
-            *reinterpret_cast<float4*>(o + j) =
-                make_float4(__fdiv_rn(__uint_as_float(w[j]), sum), __fdiv_rn(__uint_as_float(w[j + 1]), sum),
-                            __fdiv_rn(__uint_as_float(w[j + 2]), sum), __fdiv_rn(__uint_as_float(w[j + 3]), sum));
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int c4 = 0; c4 < 8; ++c4) {
+            const int j = h * 32 + c4 * 4;
+            *reinterpret_cast<float4*>(stg + h * 4096 + lane * 128 + ((c4 ^ (lane & 7)) * 16)) =
+                make_float4(__uint_as_float(w[j]) * rs, __uint_as_float(w[j + 1]) * rs, __uint_as_float(w[j + 2]) * rs,
+                            __uint_as_float(w[j + 3]) * rs);
+          }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_4d(&tm_out, smem_u32(stg), 0, x0, y0 + 4 * quad, n);
+          tma_store_4d(&tm_out, smem_u32(stg + 4096), 32, x0, y0 + 4 * quad, n);
+          tma_store_commit();
         }
         continue;  // (NT == 1: falls out of the tile loop to the stage advance below)
       }
@@ -455,7 +473,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) conv_tc_kernel(const __grid_con
      }  // tiles of the stage
       if (++as == 2) { as = 0; pacc ^= 1; }
     }
-    if (C::TMA_OUT && lane == 0) tma_store_wait_read<0>();
+    if ((C::TMA_OUT || C::OUT == 3) && lane == 0) tma_store_wait_read<0>();
   }
 
   tc_fence_before();
@@ -1129,6 +1147,19 @@ static int launch(const LayerDev& L, const __nv_bfloat16* in, void* out, int B, 
     rc = C::POOL ? encode_act_map(&tm_out, out, B, H / 2, W / 2, L.cout, 4, 2)
                  : encode_act_map(&tm_out, out, B, H, W, L.cout, 8, 4);
     if (rc != SPB_OK) return rc;
+  } else if (C::OUT == 3) {  // fp32 probabilities [B,H,W,64]: box = 32 floats x 8 pixels x 4 rows
+    EncodeTiledFn enc = get_encode();
+    cuuint64_t dims[4] = {64, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {256, (cuuint64_t)W * 256, (cuuint64_t)H * W * 256};
+    cuuint32_t box[4] = {32, 8, 4, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    const CUresult r = enc(&tm_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, out, dims, strides, box, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("conv_tc: cuTensorMapEncodeTiled(probabilities) failed with CUresult %d", (int)r);
+      return SPB_ECUDA;
+    }
   } else {
     tm_out = tm_act;
   }

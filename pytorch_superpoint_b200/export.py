@@ -48,10 +48,12 @@ class HAExporter:
                           pts_host=torch.empty((B, cap, 3), dtype=torch.float32).pin_memory(),
                           cnt_host=torch.empty((B,), dtype=torch.int32).pin_memory(),
                           done=None, mine=[]) for _ in range(2)]
-            self._bufs = {key: dict(img=torch.empty((B, H, W), device=dev, dtype=torch.float32),
+            self._bufs = {key: dict(img=[torch.empty((B, H, W), device=dev, dtype=torch.float32) for _ in range(2)],
+                                    img_free=[None, None], kin=0,
                                     sums=torch.empty((B, 2, H, W), device=dev, dtype=torch.float32),
                                     slots=slots, cap=cap, k=0)}
             self._side = torch.cuda.Stream(device=dev)
+            self._copy = torch.cuda.Stream(device=dev)
         return self._bufs[key]
 
     def heatmaps(self, imgs_dev: torch.Tensor, mats_unwarp: torch.Tensor, mats_fwd: torch.Tensor,
@@ -108,16 +110,33 @@ class HAExporter:
         return slot
 
     def submit(self, imgs_host: Sequence[torch.Tensor], mats_unwarp: torch.Tensor, mats_fwd: torch.Tensor):
-        """Host images in (pinned for true async copies): H2D + submit_resident.  Returns a ticket for collect()."""
+        """Host images in (pinned for true async copies): H2D + submit_resident.  Returns a ticket for collect().
+        The copies run on a copy stream into one of two device image buffers, so the H2D of batch i+1 overlaps the
+        kernels of batch i (the main stream only waits for its own batch's copy event)."""
         B = len(imgs_host)
         H, W = imgs_host[0].shape[-2:]
         buf = self._buffers(B, H, W)
         with torch.cuda.device(self.device):
-            for b in range(B):
-                buf["img"][b].copy_(imgs_host[b].reshape(H, W), non_blocking=True)
-            mu = mats_unwarp.to(self.device, torch.float32, non_blocking=True)
-            mf = mats_fwd.to(self.device, torch.float32, non_blocking=True)
-            return self.submit_resident(buf["img"], mu, mf)
+            j = buf["kin"] & 1
+            buf["kin"] += 1
+            img = buf["img"][j]
+            main = torch.cuda.current_stream()
+            if buf["img_free"][j] is not None:
+                self._copy.wait_event(buf["img_free"][j])  # the batch that last read this buffer has consumed it
+            with torch.cuda.stream(self._copy):
+                for b in range(B):
+                    img[b].copy_(imgs_host[b].reshape(H, W), non_blocking=True)
+                mu = mats_unwarp.to(self.device, torch.float32, non_blocking=True)
+                mf = mats_fwd.to(self.device, torch.float32, non_blocking=True)
+                copied = torch.cuda.Event()
+                copied.record(self._copy)
+            main.wait_event(copied)
+            mu.record_stream(main)
+            mf.record_stream(main)
+            ticket = self.submit_resident(img, mu, mf)
+            buf["img_free"][j] = torch.cuda.Event()
+            buf["img_free"][j].record(main)  # (after the heat-map kernels of this batch, the only readers of img)
+            return ticket
 
     def collect(self, ticket) -> List[Optional[np.ndarray]]:
         """Wait for a ticket; float64 [K,3] (x, y, conf) per image this rank owns (b % world == rank), else None."""
