@@ -233,3 +233,27 @@ def test_conv1_fused_block_equals_two_kernels(net, B, H, W):
     assert torch.isfinite(s1).all()
     assert (s0 - s1).abs().max().item() <= 1e-5  # same bf16 intermediate, same accumulation order
     assert (d0 - d1).abs().max().item() <= 1e-6
+
+
+@pytest.mark.parametrize("H,W,N", [(384, 1248, 3), (480, 640, 4), (120, 160, 7)])
+def test_ha_other_config_shapes_vs_oracle(H, W, N):
+    """BASELINE configs 3-5 shapes (KITTI 384x1248, HPatches 480x640): whole HA step vs the fp32 CPU oracle --
+    aggregated heat-map within the bf16 tolerance, mask sums bit-exact, key-points exact given the oracle's heat."""
+    from pytorch_superpoint_b200 import SuperPointNet_b200, getPtsFromHeatmap, make_ha_homographies
+    from pytorch_superpoint_b200.ops import ha_finalize
+    rng = np.random.RandomState(H + N)
+    img = np.full((H, W), 0.3, np.float32) + 0.02 * rng.randn(H, W).astype(np.float32)
+    for _ in range(24):
+        x0, y0 = rng.randint(0, W - 12), rng.randint(0, H - 12)
+        img[y0:y0 + rng.randint(6, H // 3), x0:x0 + rng.randint(6, W // 4)] = rng.uniform(0, 1)
+    img = np.clip(img, 0, 1)
+    mu, mf = make_ha_homographies(N, seed=N)
+    sd = O.synthetic_state_dict("gauss2", seed=3)
+    n = SuperPointNet_b200()
+    n.load_state_dict(sd)
+    sums = n.ha_heatmap_sums(torch.from_numpy(img).cuda(), torch.from_numpy(mu), torch.from_numpy(mf))
+    heat = ha_finalize(sums).cpu().numpy()
+    ref_pts, ref_heat = O.ha_export_one(img, mu, mf, O.canonical_params(sd), return_heat=True)
+    assert np.isfinite(heat).all() and np.abs(heat - ref_heat).max() < 1e-2
+    pts = getPtsFromHeatmap(torch.from_numpy(ref_heat).cuda(), 0.015, 4).T[:600]
+    assert np.array_equal(pts, ref_pts)
