@@ -117,6 +117,17 @@ size_t spb_nn_match_workspace_bytes(int K1, int K2);
 int spb_nn_match_two_way(const float* desc1, int K1, const float* desc2, int K2, int D, float nn_thresh, int* idx1,
                          int* idx2, float* score, int* count, void* ws, size_t ws_bytes, void* stream);
 
+/* NEXT row f-2 -- utils/homographies.py:12-141 `sample_homography_np` as called by datasets/Coco.py:262-276:
+ * `total` homographies (image b owns [b*per_image, (b+1)*per_image); index 0 of every image is the identity when
+ * per_image > 0), homographies = inv(sampled) and inv_homographies = inverse(homographies), both [total,3,3] fp32
+ * device; raw_or_null optionally receives what sample_homography_np itself returns.  Same perturbation sequence and
+ * parameter meaning as the reference (shape (2,2), shift -1); Philox counter RNG -> DISTRIBUTIONAL parity only. */
+int spb_sample_ha_homographies(unsigned long long seed, int total, int per_image, int perspective, int scaling,
+                               int rotation, int translation, int n_scales, int n_angles, double scaling_amplitude,
+                               double perspective_amplitude_x, double perspective_amplitude_y, double patch_ratio,
+                               double max_angle, int allow_artifacts, double translation_overflow,
+                               float* homographies, float* inv_homographies, float* raw_or_null, void* stream);
+
 /* ---- (2) network ------------------------------------------------------------------------------------
  * models/SuperPointNet_pretrained.py:46-76, SuperPointNet_gauss2.py:43-70, SuperPointNet.py:154-224.
  * weights/biases: HOST pointers, 12 layers in the order conv1a,1b,2a,2b,3a,3b,4a,4b,Pa,Pb,Da,Db;

@@ -5,7 +5,8 @@ Host-side mirror of the reference's interface for this path (``utils/utils.py``,
 of ``libspb200.so`` (``include/spb200.h``).  Importing the package needs neither a GPU nor the built
 library; calling any operator does, and raises otherwise -- there is no CPU fallback.
 """
-from .homographies import EXPORT_PARAMS, make_ha_homographies, sample_homography  # noqa: F401
+from .homographies import (EXPORT_PARAMS, make_ha_homographies, sample_ha_homographies_device,  # noqa: F401
+                           sample_homography)
 from .net import SuperPointNet_b200, fold_state_dict  # noqa: F401
 from .ops import (combine_heatmap, compute_valid_mask, flattenDetection, getPtsFromHeatmap,  # noqa: F401
                   inv_warp_image_batch, nn_match_two_way, sample_desc_from_points)

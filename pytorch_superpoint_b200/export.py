@@ -16,7 +16,7 @@ import torch
 import torch.distributed as dist
 
 from . import ops
-from .homographies import make_ha_homographies
+from .homographies import make_ha_homographies, sample_ha_homographies_device  # noqa: F401
 from .net import SuperPointNet_b200
 from .sharding import owner_of_image, shard_bounds, world_info
 
@@ -189,6 +189,8 @@ def export_detector_homoAdapt_b200(config, output_dir, args=None, loader=None, n
     exporter = HAExporter(net, conf_thresh, nms_dist, top_k)
     rank, world = world_info()
     count = 0
+    count_seen = 0
+    seed0 = int(config.get("seed", 0)) * 1000003  # every rank draws the same matrices for image k (shards must agree)
     for sample in loader:
         name = sample["name"][0] if not isinstance(sample["name"], str) else sample["name"]
         target = os.path.join(save_output, "{}.npz".format(name))
@@ -199,9 +201,10 @@ def export_detector_homoAdapt_b200(config, output_dir, args=None, loader=None, n
         if "homographies" in sample:
             mu = torch.as_tensor(np.asarray(sample["homographies"]), dtype=torch.float32).reshape(-1, 3, 3)
             mf = torch.as_tensor(np.asarray(sample["inv_homographies"]), dtype=torch.float32).reshape(-1, 3, 3)
-        else:
-            h, inv = make_ha_homographies(num, params=ha["homographies"]["params"])
-            mu, mf = torch.from_numpy(h), torch.from_numpy(inv)
+        else:  # drawn on the GPU (one launch; the host sampler costs ~2 s per 100 homographies, like the reference's)
+            h, inv = sample_ha_homographies_device(num, 1, seed=seed0 + count_seen, params=ha["homographies"]["params"])
+            mu, mf = h[0], inv[0]
+        count_seen += 1
         pts = exporter.export_image(img, mu, mf)
         if pts is None:
             continue

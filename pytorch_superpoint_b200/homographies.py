@@ -11,7 +11,7 @@ from math import pi
 
 import numpy as np
 
-__all__ = ["sample_homography", "make_ha_homographies", "EXPORT_PARAMS"]
+__all__ = ["sample_homography", "make_ha_homographies", "sample_ha_homographies_device", "EXPORT_PARAMS"]
 
 # configs/magicpoint_coco_export.yaml:19-28
 EXPORT_PARAMS = dict(translation=True, rotation=True, scaling=True, perspective=True,
@@ -104,3 +104,38 @@ def make_ha_homographies(num: int, seed: int | None = None, params: dict | None 
     hs = torch.tensor(hs, dtype=torch.float32)
     inv = torch.stack([torch.inverse(hs[i]) for i in range(num)])
     return hs.numpy(), inv.numpy()
+
+
+def sample_ha_homographies_device(num: int, images: int = 1, seed: int = 0, params: dict | None = None, device=None,
+                                  return_raw: bool = False):
+    """GPU form of datasets/Coco.py:262-276 for a whole batch: ``images`` x ``num`` homographies drawn by one kernel
+    launch (libspb200 ``spb_sample_ha_homographies``; Philox counters, so a (seed, index) pair is reproducible but the
+    stream differs from numpy's -- distributional parity with ``utils/homographies.py:12-141``).
+
+    Returns cuda float32 ``(homographies, inv_homographies)`` of shape ``[images, num, 3, 3]`` with
+    ``homographies[:, 0] = I`` (and the raw ``sample_homography_np`` matrices when ``return_raw``).  The host sampler
+    above needs ~20 ms per homography (a scipy ``truncnorm`` object per draw, like the reference); this one is what
+    ``export_detector_homoAdapt_b200`` uses when the data loader does not provide the matrices."""
+    import torch
+
+    from . import _lib
+    if not torch.cuda.is_available():
+        raise RuntimeError("sample_ha_homographies_device needs a CUDA device (sm_100a); there is no CPU fallback")
+    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    p = dict(perspective=True, scaling=True, rotation=True, translation=True, n_scales=5, n_angles=25,
+             scaling_amplitude=0.1, perspective_amplitude_x=0.1, perspective_amplitude_y=0.1, patch_ratio=0.5,
+             max_angle=pi / 2, allow_artifacts=False, translation_overflow=0.0)  # defaults of sample_homography_np
+    p.update(EXPORT_PARAMS if params is None else params)
+    total = int(images) * int(num)
+    h = torch.empty((images, num, 3, 3), dtype=torch.float32, device=dev)
+    inv = torch.empty_like(h)
+    raw = torch.empty_like(h) if return_raw else None
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().spb_sample_ha_homographies(
+            int(seed) & 0xFFFFFFFFFFFFFFFF, total, int(num), int(bool(p["perspective"])), int(bool(p["scaling"])),
+            int(bool(p["rotation"])), int(bool(p["translation"])), int(p["n_scales"]), int(p["n_angles"]),
+            float(p["scaling_amplitude"]), float(p["perspective_amplitude_x"]), float(p["perspective_amplitude_y"]),
+            float(p["patch_ratio"]), float(p["max_angle"]), int(bool(p["allow_artifacts"])),
+            float(p["translation_overflow"]), h.data_ptr(), inv.data_ptr(), raw.data_ptr() if return_raw else None,
+            torch.cuda.current_stream().cuda_stream), "sample_ha_homographies")
+    return (h, inv, raw) if return_raw else (h, inv)

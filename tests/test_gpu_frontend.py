@@ -150,3 +150,70 @@ def test_nn_match_two_way_edge_cases():
     d[0] = 1.0
     m = nn_match_two_way(d, d, 0.5)
     assert np.array_equal(m, O.nn_match_two_way(d, d, 0.5))
+
+
+def _patch_corners(raw):
+    """sample_homography_np's matrix maps the corners of the [-1,1]^2 frame to the sampled patch corners."""
+    c = np.array([[-1, -1, 1], [-1, 1, 1], [1, 1, 1], [1, -1, 1]], np.float64)
+    q = np.einsum("kij,cj->kci", raw.astype(np.float64), c)
+    return (q[..., :2] / q[..., 2:]).reshape(len(raw), 8)
+
+
+@pytest.mark.parametrize("name", ["export", "noartifacts"])
+def test_device_sampler_distribution_vs_reference_draws(golden, name):
+    """f-2: the GPU sampler draws from the same distribution as the reference's sample_homography_np (3000 draws of
+    the unmodified reference in tests/golden/sampler_draws.npz): per patch-corner coordinate KS two-sample test,
+    means and spreads."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from scipy.stats import ks_2samp
+    from pytorch_superpoint_b200 import EXPORT_PARAMS, sample_ha_homographies_device
+    params = dict(EXPORT_PARAMS)
+    if name == "noartifacts":
+        params.update(allow_artifacts=False, patch_ratio=0.5, scaling_amplitude=0.4, perspective_amplitude_x=0.3,
+                      perspective_amplitude_y=0.3)
+    ref = _patch_corners(golden("sampler_draws")[name])
+    _, _, raw = sample_ha_homographies_device(20000, 1, seed=11, params=params, return_raw=True)
+    got = _patch_corners(raw[0].cpu().numpy())
+    assert np.isfinite(got).all()
+    for j in range(8):
+        ks = ks_2samp(ref[:, j], got[:, j]).statistic
+        assert ks < 0.045, f"coordinate {j}: KS statistic {ks:.3f}"  # alpha = 1e-3 critical value is 0.038 + margin
+        s = ref[:, j].std()
+        assert abs(ref[:, j].mean() - got[:, j].mean()) < 5 * s / np.sqrt(len(ref))
+        assert 0.93 < got[:, j].std() / s < 1.07
+    if name == "noartifacts":  # without artifacts every patch stays inside the frame
+        assert np.abs(got).max() <= 1.0 + 1e-6
+
+
+def test_device_sampler_structure_and_export_without_loader_matrices(tmp_path):
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from pytorch_superpoint_b200 import SuperPointNet_b200, sample_ha_homographies_device
+    from pytorch_superpoint_b200.export import export_detector_homoAdapt_b200
+    h, inv, raw = sample_ha_homographies_device(7, 3, seed=5, return_raw=True)
+    assert tuple(h.shape) == (3, 7, 3, 3) and h.dtype == torch.float32 and h.is_cuda
+    eye = torch.eye(3, device="cuda")
+    assert torch.equal(h[:, 0], eye.expand(3, 3, 3)) and torch.equal(inv[:, 0], eye.expand(3, 3, 3))
+    assert (h.double() @ inv.double() - eye.double()).abs().max().item() < 1e-5     # Coco.py:276
+    assert (raw[:, 1:].double() @ h[:, 1:].double() - eye.double()).abs().max().item() < 1e-5  # Coco.py:268
+    h2, _ = sample_ha_homographies_device(7, 3, seed=5)
+    assert torch.equal(h, h2)                                                        # (seed, index) reproducible
+    h3, _ = sample_ha_homographies_device(21, 1, seed=5)
+    assert torch.equal(h3[0, 1:7], h[0, 1:7]) and torch.equal(h3[0, 8:14], h[1, 1:7])  # counter-based: index only
+    assert not torch.equal(sample_ha_homographies_device(7, 3, seed=6)[0], h)
+    # the .npz entry point draws its own matrices when the loader provides none
+    net = SuperPointNet_b200()
+    net.load_state_dict(O.synthetic_state_dict("gauss2", seed=2))
+    rng = np.random.RandomState(4)
+    samples = [{"image_2D": torch.from_numpy(rng.rand(1, 1, 64, 96).astype(np.float32)), "name": [f"a{i}"]}
+               for i in range(2)]
+    cfg = {"model": {"nms": 4, "top_k": 50, "detection_threshold": 0.015, "subpixel": {"enable": False}},
+           "data": {"export_folder": "train", "dataset": "Coco",
+                    "homography_adaptation": {"num": 6, "homographies": {"params": {
+                        "translation": True, "rotation": True, "scaling": True, "perspective": True,
+                        "scaling_amplitude": 0.2, "perspective_amplitude_x": 0.2, "perspective_amplitude_y": 0.2,
+                        "allow_artifacts": True, "patch_ratio": 0.85}}}}}
+    assert export_detector_homoAdapt_b200(cfg, str(tmp_path), loader=samples, net=net) == 2
+    pts = np.load(os.path.join(str(tmp_path), "predictions", "train", "a0.npz"))["pts"]
+    assert pts.dtype == np.float64 and pts.shape[1] == 3 and 0 < pts.shape[0] <= 50
