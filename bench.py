@@ -184,11 +184,13 @@ def run_b200(args):
     exporter = HAExporter(net, THR, NMS, TOPK, device=dev, chunk=args.chunk)
     B = args.images
     imgs_np = structured_images(B, seed=0)
-    mu_np, mf_np = make_ha_homographies(NVIEWS, seed=0)  # pre-sampled outside the timed region
+    # every image gets its OWN 100 homographies, like datasets/Coco.py:262-276.  Resident arm: pre-sampled outside
+    # the timed region.  End-to-end arm: drawn afresh on the GPU inside every step (sampler.cu; all
+    # ranks use the same counter-based seed, so the shards agree on the matrices).
+    from pytorch_superpoint_b200.homographies import sample_ha_homographies_device
     imgs_host = [torch.from_numpy(imgs_np[b]).pin_memory() for b in range(B)]
-    mu_host, mf_host = torch.from_numpy(mu_np).pin_memory(), torch.from_numpy(mf_np).pin_memory()
     imgs_dev = torch.from_numpy(imgs_np).to(dev)
-    mu_dev, mf_dev = mu_host.to(dev), mf_host.to(dev)
+    mu_dev, mf_dev = sample_ha_homographies_device(NVIEWS, B, seed=0, device=dev)
     from pytorch_superpoint_b200 import ops
 
     def step_resident():
@@ -226,11 +228,14 @@ def run_b200(args):
 
     # ---- end to end through the public API: pinned host images in, host key-points out ------------------
     pending = []
+    e2e_seen = []
 
     def step_e2e():
         # pinned host images in -> host key-points out; batch i's NMS + D2H overlap batch i+1, results of batch
         # i-1 are collected (host numpy arrays) while batch i runs
-        pending.append(exporter.submit(imgs_host, mu_host, mf_host))
+        mu_step, mf_step = sample_ha_homographies_device(NVIEWS, B, seed=1 + len(e2e_seen), device=dev)
+        e2e_seen.append(0)
+        pending.append(exporter.submit(imgs_host, mu_step, mf_step))
         if len(pending) > 1:
             exporter.collect(pending.pop(0))
 
@@ -260,7 +265,7 @@ def run_b200(args):
 
     ms_e2e = timed_e2e(args.steps)
     e2e_value = B * args.steps / (ms_e2e / 1e3)
-    h2d = B * H * W * 4 + 2 * NVIEWS * 9 * 4
+    h2d = B * H * W * 4  # the homographies are drawn on the device
     d2h = -(-B // world) * (TOPK * 3 * 4 + 4)
 
     # ---- roofline of the dominant kernel: a profiled pass (CUDA events around every stage launch) -------
@@ -300,6 +305,8 @@ def run_b200(args):
             "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "images_per_step": B, "homographies": NVIEWS,
+                       "homography_sets": "one set of 100 per image (datasets/Coco.py:262-276); resident arm: pre-sampled; "
+                                          "e2e arm: drawn on the GPU inside every step",
                        "parallelism": f"homography-sharded x{world}, 1 NCCL all-reduce of [B,2,H,W] per step",
                        "l2": "per-image activation working set ~1.3 GB streams through the 126 MB L2 every step "
                              "(inputs larger than L2; no explicit flush)", "ha_chunk": args.chunk},
@@ -313,6 +320,7 @@ def run_b200(args):
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
         params = O.canonical_params(synthetic_state_dict("gauss2", seed=1))
+        mu_np, mf_np = mu_dev[0].cpu().numpy(), mf_dev[0].cpu().numpy()  # image 0's matrices, same on both sides
         cpu_step(params, imgs_np[0], mu_np, mf_np, 5)  # warm-up
         t0 = time.perf_counter()
         pts_cpu = cpu_step(params, imgs_np[0], mu_np, mf_np, NVIEWS)
@@ -321,7 +329,7 @@ def run_b200(args):
                                 "sample": "one full 240x320 image with all 100 homographies through oracle/ "
                                           "(numpy warp/mask/combine/NMS + torch fp32 conv on all host threads)"}
         # the same image through the GPU path: key-point overlap with the fp32 CPU oracle (informational)
-        pts_gpu = exporter.export_image(imgs_host[0], mu_host, mf_host)
+        pts_gpu = exporter.export_image(imgs_host[0], mu_dev[0], mf_dev[0])
         a = {(int(x), int(y)) for x, y, _ in pts_gpu}
         b = {(int(x), int(y)) for x, y, _ in pts_cpu}
         line["keypoint_jaccard_vs_cpu_fp32"] = round(len(a & b) / max(len(a | b), 1), 4)
