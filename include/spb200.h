@@ -101,6 +101,18 @@ int spb_get_pts_from_heatmap(const float* heat, int B, int H, int W, float conf_
 int spb_sample_desc_from_points(const float* coarse, int nhwc, const float* pts, const int* count, int K,
                                 int Hc, int Wc, int D, int cell, float* out, void* stream);
 
+/* Same with the point row stride (2 = (x, y), 3 = (x, y, conf)) and the final L2 normalisation optional: the batched
+ * variant models/model_utils.py:63-90 (SuperPointNet_process.sample_desc_from_points) returns the raw samples. */
+int spb_sample_desc_from_points_ex(const float* coarse, int nhwc, const float* pts, int pts_stride, const int* count,
+                                   int K, int Hc, int Wc, int D, int cell, int normalize, float* out, void* stream);
+
+/* NEXT row f-3 -- models/model_utils.py:24-60 `SuperPointNet_process.pred_soft_argmax`: 5x5 roi_pool patches of the
+ * 7x7 window around every labelled pixel (utils/losses.py:16-29,87-98 + torchvision roi_pool bin rule), log, spatial
+ * soft-argmax in pixel coordinates (torchgeometry restated: parity unpinned).  heat [B,1,H,W] fp32, idx [N,4] int64
+ * rows (batch, 0, y, x) as produced by labels.nonzero(); dxdy [N,2]; patches_or_null [N,25]. */
+int spb_roi_soft_argmax(const float* heat, int B, int H, int W, const long long* idx, int N, float* dxdy,
+                        float* patches_or_null, void* stream);
+
 /* NEXT row f-1b -- models/model_wrap.py:200-234 `soft_argmax_points` (+ utils/losses.py:48-129): per key-point
  * soft-argmax offset over the patch_size x patch_size (odd, <= 7) heat-map patch.  dxdy [K,2] fp32; the
  * refined point is (x + dx - patch_size/2, y + dy - patch_size/2).  torchgeometry's SpatialSoftArgmax2d is

@@ -34,6 +34,8 @@ PROTOTYPES = {
     "spb_nms_workspace_bytes": (_z, [_i, _i, _i, _i]),
     "spb_get_pts_from_heatmap": (_i, [_p, _i, _i, _i, _f, _i, _i, _i, _i, _p, _p, _p, _p, _z, _p]),
     "spb_sample_desc_from_points": (_i, [_p, _i, _p, _p, _i, _i, _i, _i, _i, _p, _p]),
+    "spb_sample_desc_from_points_ex": (_i, [_p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _p, _p]),
+    "spb_roi_soft_argmax": (_i, [_p, _i, _i, _i, _p, _i, _p, _p, _p]),
     "spb_soft_argmax_points": (_i, [_p, _i, _i, _p, _p, _i, _i, _p, _p]),
     "spb_nn_match_workspace_bytes": (_z, [_i, _i]),
     "spb_nn_match_two_way": (_i, [_p, _i, _p, _i, _i, _f, _p, _p, _p, _p, _p, _z, _p]),

@@ -9,16 +9,19 @@
 
 namespace spb {
 
+// stride: floats per point in pts (3 for (x, y, conf) rows, 2 for (x, y)); normalize = 0 keeps the raw bilinear
+// sample (models/model_utils.py:63-90, the batched deepFEPE-facing variant, does not re-normalise)
 template <bool NHWC>
 __global__ void __launch_bounds__(256) sample_desc_kernel(const float* __restrict__ coarse,
                                                           const float* __restrict__ pts,
                                                           const int* __restrict__ count, int K, int Hc, int Wc,
-                                                          int D, int cell, float* __restrict__ out) {
+                                                          int D, int cell, float* __restrict__ out, int stride,
+                                                          int normalize) {
   const int lane = threadIdx.x & 31;
   const int k = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int n = count ? min(*count, K) : K;
   if (k >= n) return;
-  const double x = (double)pts[3 * k], y = (double)pts[3 * k + 1];
+  const double x = (double)pts[stride * k], y = (double)pts[stride * k + 1];
   const double halfw = (double)((float)(Wc * cell)) / 2.0, halfh = (double)((float)(Hc * cell)) / 2.0;
   const float gx = (float)(x / halfw - 1.0), gy = (float)(y / halfh - 1.0);
   const float ix = __fmul_rn(__fdiv_rn(__fadd_rn(gx, 1.f), 2.f), (float)(Wc - 1));
@@ -33,6 +36,7 @@ __global__ void __launch_bounds__(256) sample_desc_kernel(const float* __restric
     o[c] = v;
     ss = __fmaf_rn(v, v, ss);
   }
+  if (!normalize) return;
   ss = warp_sum(ss);
   const float nrm = sqrtf(ss);
   __syncwarp();
@@ -43,18 +47,26 @@ __global__ void __launch_bounds__(256) sample_desc_kernel(const float* __restric
 
 using namespace spb;
 
-extern "C" int spb_sample_desc_from_points(const float* coarse, int nhwc, const float* pts, const int* count, int K,
-                                           int Hc, int Wc, int D, int cell, float* out, void* stream) {
+extern "C" int spb_sample_desc_from_points_ex(const float* coarse, int nhwc, const float* pts, int pts_stride,
+                                              const int* count, int K, int Hc, int Wc, int D, int cell, int normalize,
+                                              float* out, void* stream) {
   SPB_CHECK_ARG(coarse && pts && out);
-  SPB_CHECK_ARG(K >= 0 && Hc >= 2 && Wc >= 2 && D >= 1 && cell >= 1);
+  SPB_CHECK_ARG(K >= 0 && Hc >= 2 && Wc >= 2 && D >= 1 && cell >= 1 && pts_stride >= 2);
   if (K == 0) return SPB_OK;
   const int blocks = ceil_div(K, 8);
   if (nhwc)
-    sample_desc_kernel<true><<<blocks, 256, 0, as_stream(stream)>>>(coarse, pts, count, K, Hc, Wc, D, cell, out);
+    sample_desc_kernel<true><<<blocks, 256, 0, as_stream(stream)>>>(coarse, pts, count, K, Hc, Wc, D, cell, out,
+                                                                    pts_stride, normalize);
   else
-    sample_desc_kernel<false><<<blocks, 256, 0, as_stream(stream)>>>(coarse, pts, count, K, Hc, Wc, D, cell, out);
+    sample_desc_kernel<false><<<blocks, 256, 0, as_stream(stream)>>>(coarse, pts, count, K, Hc, Wc, D, cell, out,
+                                                                     pts_stride, normalize);
   SPB_CHECK_LAUNCH();
   return SPB_OK;
+}
+
+extern "C" int spb_sample_desc_from_points(const float* coarse, int nhwc, const float* pts, const int* count, int K,
+                                           int Hc, int Wc, int D, int cell, float* out, void* stream) {
+  return spb_sample_desc_from_points_ex(coarse, nhwc, pts, 3, count, K, Hc, Wc, D, cell, 1, out, stream);
 }
 
 // ---- sub-pixel refinement (NEXT row f-1b): models/model_wrap.py:200-234 + utils/losses.py:48-129 ------------
@@ -104,6 +116,61 @@ extern "C" int spb_soft_argmax_points(const float* heat, int H, int W, const flo
   if (K == 0) return SPB_OK;
   spb::soft_argmax_kernel<<<spb::ceil_div(K, 128), 128, 0, spb::as_stream(stream)>>>(heat, H, W, pts, count, K,
                                                                                      patch_size, dxdy);
+  SPB_CHECK_LAUNCH();
+  return SPB_OK;
+}
+
+
+// ---- NEXT row f-3: models/model_utils.py:24-60 pred_soft_argmax -------------------------------------------
+// Patches as utils/losses.py:16-29,87-98 builds them: box (x-3, y-3, x+3, y+3) around every labelled pixel,
+// torchvision roi_pool to 5x5 (a 7-pixel span in 5 bins of 1.4: rows/cols {0,1},{1,2},{2,3,4},{4,5},{5,6}, max over
+// each bin, bins clipped to the image), then log (negatives -> 1e-6) and torchgeometry's SpatialSoftArgmax2d in
+// pixel coordinates (restated, parity unpinned as in f-1b).  idx [N,4] int64 rows (batch, channel, y, x) = the
+// rows of labels.nonzero(); heat [B,1,H,W].  dxdy [N,2] = soft-argmax position (caller subtracts patch//2).
+namespace spb {
+__global__ void __launch_bounds__(128) roi_soft_argmax_kernel(const float* __restrict__ heat, int H, int W,
+                                                              const long long* __restrict__ idx, int N,
+                                                              float* __restrict__ dxdy, float* __restrict__ patches) {
+  const int k = blockIdx.x * 128 + threadIdx.x;
+  if (k >= N) return;
+  const long long b = idx[4 * k];
+  const int y = (int)idx[4 * k + 2], x = (int)idx[4 * k + 3];
+  const float* img = heat + b * H * W;
+  const int lo[5] = {0, 1, 2, 4, 5}, hi[5] = {2, 3, 5, 6, 7};  // floor(p*1.4), ceil((p+1)*1.4)
+  float v[25];
+  float mx = -INFINITY;
+  for (int py = 0; py < 5; ++py)
+    for (int px = 0; px < 5; ++px) {
+      const int y0 = min(max(y - 3 + lo[py], 0), H), y1 = min(max(y - 3 + hi[py], 0), H);
+      const int x0 = min(max(x - 3 + lo[px], 0), W), x1 = min(max(x - 3 + hi[px], 0), W);
+      float m = (y1 <= y0 || x1 <= x0) ? 0.f : -INFINITY;  // empty bin -> 0 (torchvision)
+      for (int yy = y0; yy < y1; ++yy)
+        for (int xx = x0; xx < x1; ++xx) m = fmaxf(m, __ldg(img + (long long)yy * W + xx));
+      if (patches) patches[(long long)k * 25 + py * 5 + px] = m;
+      const float q = m < 0.f ? 1e-6f : m;
+      v[py * 5 + px] = logf(q);
+      mx = fmaxf(mx, v[py * 5 + px]);
+    }
+  float se = 0.f, sx = 0.f, sy = 0.f;
+  for (int i = 0; i < 25; ++i) {
+    const float e = expf(v[i] - mx);
+    se += e;
+    sx += (float)(i % 5) * e;
+    sy += (float)(i / 5) * e;
+  }
+  const float inv = __fdiv_rn(1.f, se + 1e-6f);
+  dxdy[2 * k] = sx * inv;
+  dxdy[2 * k + 1] = sy * inv;
+}
+}  // namespace spb
+
+extern "C" int spb_roi_soft_argmax(const float* heat, int B, int H, int W, const long long* idx, int N, float* dxdy,
+                                   float* patches_or_null, void* stream) {
+  SPB_CHECK_ARG(heat && dxdy && B >= 1 && H > 0 && W > 0 && N >= 0);
+  if (N == 0) return SPB_OK;
+  SPB_CHECK_ARG(idx != nullptr);
+  spb::roi_soft_argmax_kernel<<<spb::ceil_div(N, 128), 128, 0, spb::as_stream(stream)>>>(heat, H, W, idx, N, dxdy,
+                                                                                         patches_or_null);
   SPB_CHECK_LAUNCH();
   return SPB_OK;
 }

@@ -162,6 +162,19 @@ class SuperPointNet_b200(nn.Module):
         self.output = output
         return output
 
+    def process_output(self, sp_processer):
+        """models/SuperPointNet_gauss2.py:72-99: after forward(), flatten -> NMS -> soft-argmax residuals -> fixed
+        number of (points, residuals, descriptors) per image; ``sp_processer`` is a SuperPointNet_process_b200."""
+        from .ops import flattenDetection
+        output = self.output
+        semi, desc = output["semi"], output["desc"]
+        heatmap = flattenDetection(semi.contiguous(), True)
+        heatmap_nms_batch = sp_processer.heatmap_to_nms(heatmap, tensor=True)
+        residual = sp_processer.pred_soft_argmax(heatmap_nms_batch, heatmap)["pred"]
+        output.update(sp_processer.batch_extract_features(desc, heatmap_nms_batch, residual))
+        self.output = output
+        return output
+
     # ---- whole HA step (datasets/Coco.py:262-284 + export.py:309-310) -----------------------------------
     def ha_heatmap_sums(self, img, mats_unwarp, mats_fwd, sums=None, accumulate=False, chunk: int = 0):
         """img [H,W] cuda fp32; mats [N,3,3] (this rank's views) -> sums [2,H,W] (sum heat*mask, sum mask)."""

@@ -217,3 +217,51 @@ def test_device_sampler_structure_and_export_without_loader_matrices(tmp_path):
     assert export_detector_homoAdapt_b200(cfg, str(tmp_path), loader=samples, net=net) == 2
     pts = np.load(os.path.join(str(tmp_path), "predictions", "train", "a0.npz"))["pts"]
     assert pts.dtype == np.float64 and pts.shape[1] == 3 and 0 < pts.shape[0] <= 50
+
+
+def test_superpointnet_process_vs_reference_golden(golden):
+    """f-3: SuperPointNet_process (models/model_utils.py) on the GPU vs golden outputs of the unmodified reference:
+    NMS mask and roi-pooled patches bit-exact, raw descriptor samples and the cropped/padded feature batch (same
+    seeded numpy RNG calls) to fp32 round-off."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from pytorch_superpoint_b200.process import SuperPointNet_process_b200
+    g = golden("process")
+    proc = SuperPointNet_process_b200(out_num_points=60, patch_size=5, device="cuda:0", nms_dist=4, conf_thresh=0.015)
+    heat = torch.from_numpy(g["heat"]).cuda()
+    mask = proc.heatmap_to_nms(heat, tensor=True)
+    assert mask.is_cuda and np.array_equal(mask.cpu().numpy(), g["mask"])
+    assert np.array_equal(proc.heatmap_to_nms(heat, tensor=False), g["mask"])
+    out = proc.pred_soft_argmax(mask, heat)
+    assert np.array_equal(out["patches"].cpu().numpy(), g["patches"])                      # roi_pool bins, pinned
+    pred = out["pred"].cpu().numpy()
+    assert pred.shape == (g["idx"].shape[0], 2) and np.isfinite(pred).all() and np.abs(pred).max() <= 2.0
+    # the soft-argmax of log(patch) is the probability-weighted centroid of the patch (torchgeometry restated)
+    p = g["patches"][:, 0].astype(np.float64)
+    gx, gy = np.meshgrid(np.arange(5), np.arange(5))
+    cen = np.stack([(p * gx).sum((1, 2)), (p * gy).sum((1, 2))], 1) / p.sum((1, 2))[:, None] - 2
+    assert np.abs(pred - cen).max() < 1e-4
+    desc = torch.from_numpy(g["desc"]).cuda()
+    samp = proc.sample_desc_from_points(desc[:1], torch.from_numpy(g["pts"]).cuda())
+    assert tuple(samp.shape) == g["samp"].shape and np.abs(samp.cpu().numpy() - g["samp"]).max() < 2e-6
+    np.random.seed(99)
+    feat = proc.batch_extract_features(desc, mask, torch.from_numpy(g["residual"]).cuda())
+    assert np.array_equal(feat["pts_int"].cpu().numpy(), g["pts_int"])
+    assert np.array_equal(feat["pts_offset"].cpu().numpy(), g["pts_offset"])
+    assert np.abs(feat["pts_desc"].cpu().numpy() - g["pts_desc"]).max() < 2e-6
+
+
+def test_process_output_end_to_end():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from pytorch_superpoint_b200 import SuperPointNet_b200
+    from pytorch_superpoint_b200.process import SuperPointNet_process_b200
+    net = SuperPointNet_b200()
+    net.load_state_dict(O.synthetic_state_dict("gauss2", seed=2))
+    x = torch.rand(2, 1, 64, 96, generator=torch.Generator().manual_seed(3)).cuda()
+    net(x)
+    np.random.seed(0)
+    out = net.process_output(SuperPointNet_process_b200(out_num_points=80, device="cuda:0"))
+    assert tuple(out["pts_int"].shape) == (2, 80, 2) and tuple(out["pts_offset"].shape) == (2, 80, 2)
+    assert tuple(out["pts_desc"].shape) == (2, 80, 256) and torch.isfinite(out["pts_desc"]).all()
+    assert out["pts_int"][..., 0].max() < 96 and out["pts_int"][..., 1].max() < 64
