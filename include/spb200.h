@@ -113,6 +113,11 @@ int spb_sample_desc_from_points_ex(const float* coarse, int nhwc, const float* p
 int spb_roi_soft_argmax(const float* heat, int B, int H, int W, const long long* idx, int N, float* dxdy,
                         float* patches_or_null, void* stream);
 
+/* NEXT row f-4 (dense-descriptor mode) -- models/model_wrap.py:393-401: bilinear x`cell` up-sampling of the coarse
+ * descriptors (F.interpolate, align_corners=False) fused with the channel L2 normalisation.
+ * coarse NHWC [B,Hc,Wc,D] fp32 (D % 8 == 0, D <= 256) -> dense NCHW [B,D,Hc*cell,Wc*cell] fp32. */
+int spb_dense_desc(const float* coarse_nhwc, int B, int Hc, int Wc, int D, int cell, float* dense_nchw, void* stream);
+
 /* NEXT row f-1b -- models/model_wrap.py:200-234 `soft_argmax_points` (+ utils/losses.py:48-129): per key-point
  * soft-argmax offset over the patch_size x patch_size (odd, <= 7) heat-map patch.  dxdy [K,2] fp32; the
  * refined point is (x + dx - patch_size/2, y + dy - patch_size/2).  torchgeometry's SpatialSoftArgmax2d is

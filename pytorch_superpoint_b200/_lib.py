@@ -36,6 +36,7 @@ PROTOTYPES = {
     "spb_sample_desc_from_points": (_i, [_p, _i, _p, _p, _i, _i, _i, _i, _i, _p, _p]),
     "spb_sample_desc_from_points_ex": (_i, [_p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _p, _p]),
     "spb_roi_soft_argmax": (_i, [_p, _i, _i, _i, _p, _i, _p, _p, _p]),
+    "spb_dense_desc": (_i, [_p, _i, _i, _i, _i, _i, _p, _p]),
     "spb_soft_argmax_points": (_i, [_p, _i, _i, _p, _p, _i, _i, _p, _p]),
     "spb_nn_match_workspace_bytes": (_z, [_i, _i]),
     "spb_nn_match_two_way": (_i, [_p, _i, _p, _i, _i, _f, _p, _p, _p, _p, _p, _z, _p]),

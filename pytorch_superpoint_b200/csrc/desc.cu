@@ -174,3 +174,56 @@ extern "C" int spb_roi_soft_argmax(const float* heat, int B, int H, int W, const
   SPB_CHECK_LAUNCH();
   return SPB_OK;
 }
+
+
+// ---- NEXT row f-4 (dense-descriptor mode of run()): models/model_wrap.py:393-401 ----------------------------
+// dense = F.interpolate(coarse, scale_factor=(cell, cell), mode='bilinear')  (align_corners=False: source index
+// (dst + 0.5)/cell - 0.5 clamped at 0, second tap clamped to the last cell), then dense / ||dense||_2 over the
+// channels.  coarse NHWC [B,Hc,Wc,D] (our network's layout), dense NCHW [B,D,H,W] (the reference's layout).
+// Block = 32 consecutive pixels of one row x 8 channel groups: every channel plane is written in 128-byte
+// segments; the squared norm is reduced over the channel groups through shared memory.
+namespace spb {
+__global__ void __launch_bounds__(256) dense_desc_kernel(const float* __restrict__ coarse, float* __restrict__ dense,
+                                                         int Hc, int Wc, int D, int cell) {
+  __shared__ float ss[8][33];
+  const int W = Wc * cell, H = Hc * cell;
+  const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y, b = blockIdx.z, g = threadIdx.y;
+  const int xx = x < W ? x : W - 1;
+  const float inv = 1.f / (float)cell;
+  const float sx = fmaxf(__fsub_rn(__fmul_rn(inv, __fadd_rn((float)xx, 0.5f)), 0.5f), 0.f);
+  const float sy = fmaxf(__fsub_rn(__fmul_rn(inv, __fadd_rn((float)y, 0.5f)), 0.5f), 0.f);
+  const int x0 = (int)sx, y0 = (int)sy, x1 = min(x0 + 1, Wc - 1), y1 = min(y0 + 1, Hc - 1);
+  const float lx = sx - (float)x0, ly = sy - (float)y0, mx = 1.f - lx, my = 1.f - ly;
+  const float* c00 = coarse + (((long long)b * Hc + y0) * Wc + x0) * D;
+  const float* c01 = coarse + (((long long)b * Hc + y0) * Wc + x1) * D;
+  const float* c10 = coarse + (((long long)b * Hc + y1) * Wc + x0) * D;
+  const float* c11 = coarse + (((long long)b * Hc + y1) * Wc + x1) * D;
+  const int per = D / 8;  // channels per group (D % 8 == 0, per <= 32)
+  float v[32];
+  float acc = 0.f;
+  for (int j = 0; j < per; ++j) {
+    const int c = g * per + j;
+    v[j] = my * (mx * __ldg(c00 + c) + lx * __ldg(c01 + c)) + ly * (mx * __ldg(c10 + c) + lx * __ldg(c11 + c));
+    acc = fmaf(v[j], v[j], acc);
+  }
+  ss[g][threadIdx.x] = acc;
+  __syncthreads();
+  float tot = 0.f;
+  for (int k = 0; k < 8; ++k) tot += ss[k][threadIdx.x];
+  const float nrm = sqrtf(tot);
+  if (x < W) {
+    float* o = dense + (((long long)b * D + g * per) * H + y) * W + x;
+    for (int j = 0; j < per; ++j) o[(long long)j * H * W] = __fdiv_rn(v[j], nrm);
+  }
+}
+}  // namespace spb
+
+extern "C" int spb_dense_desc(const float* coarse_nhwc, int B, int Hc, int Wc, int D, int cell, float* dense_nchw,
+                              void* stream) {
+  SPB_CHECK_ARG(coarse_nhwc && dense_nchw && B >= 1 && Hc >= 1 && Wc >= 1 && cell >= 1);
+  SPB_CHECK_ARG(D >= 8 && D % 8 == 0 && D <= 256 && Hc * cell <= 65535 && B <= 65535);
+  dim3 grid(spb::ceil_div(Wc * cell, 32), Hc * cell, B), block(32, 8);
+  spb::dense_desc_kernel<<<grid, block, 0, spb::as_stream(stream)>>>(coarse_nhwc, dense_nchw, Hc, Wc, D, cell);
+  SPB_CHECK_LAUNCH();
+  return SPB_OK;
+}

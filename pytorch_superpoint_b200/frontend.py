@@ -142,12 +142,20 @@ class SuperPointFrontend_b200(object):
         p = p.cpu().numpy().astype(np.float64)
         pts = [p[i, :counts[i]].T.copy() for i in range(B)]
         self.pts = pts
-        coarse = desc.permute(0, 3, 1, 2)
-        dense = torch.nn.functional.interpolate(coarse, scale_factor=(self.cell, self.cell), mode="bilinear")
-        dense = dense / torch.norm(dense, p=2, dim=1, keepdim=True)
-        dense_cpu = dense.cpu().numpy()
-        pts_desc = [dense_cpu[i, :, pts[i][1, :].astype(int), pts[i][0, :].astype(int)].transpose()
-                    for i in range(B)]
+        # models/model_wrap.py:393-404: dense = normalise(interpolate(coarse, x8)); one fused kernel, and only the
+        # key-point columns (not the 78 MB/image dense tensor) travel to the host
+        D = desc.shape[-1]
+        dense = torch.empty((B, D, H, W), device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().spb_dense_desc(desc.data_ptr(), B, H // self.cell, W // self.cell, D, self.cell,
+                                                 dense.data_ptr(), torch.cuda.current_stream().cuda_stream),
+                       "dense_desc")
+        pts_desc = []
+        for i in range(B):
+            yy = torch.as_tensor(pts[i][1, :].astype(np.int64), device=dev)
+            xx = torch.as_tensor(pts[i][0, :].astype(np.int64), device=dev)
+            # (numpy's dense_cpu[i, :, ys, xs].transpose() in the reference comes out as [D, K]; same here)
+            pts_desc.append(dense[i][:, yy, xx].cpu().numpy())
         if self.subpixel:
             raise NotImplementedError("residual sub-pixel head (SubpixelNet) is outside the hot path")
         return pts, pts_desc, dense, heat

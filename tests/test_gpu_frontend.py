@@ -265,3 +265,22 @@ def test_process_output_end_to_end():
     assert tuple(out["pts_int"].shape) == (2, 80, 2) and tuple(out["pts_offset"].shape) == (2, 80, 2)
     assert tuple(out["pts_desc"].shape) == (2, 80, 256) and torch.isfinite(out["pts_desc"]).all()
     assert out["pts_int"][..., 0].max() < 96 and out["pts_int"][..., 1].max() < 64
+
+
+@pytest.mark.parametrize("B,Hc,Wc", [(2, 8, 12), (1, 30, 40), (3, 5, 7)])
+def test_dense_desc_vs_torch(B, Hc, Wc):
+    """f-4 dense-descriptor mode (models/model_wrap.py:393-401): fused x8 bilinear up-sampling + L2 normalisation vs
+    torch's F.interpolate + norm on the same fp32 input."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from pytorch_superpoint_b200 import _lib
+    g = torch.Generator().manual_seed(Hc)
+    coarse = torch.randn(B, 256, Hc, Wc, generator=g)
+    coarse = coarse / coarse.norm(dim=1, keepdim=True)
+    ref = torch.nn.functional.interpolate(coarse, scale_factor=(8, 8), mode="bilinear")
+    ref = ref / torch.norm(ref, p=2, dim=1, keepdim=True)
+    nhwc = coarse.permute(0, 2, 3, 1).contiguous().cuda()
+    dense = torch.full((B, 256, Hc * 8, Wc * 8), float("nan"), device="cuda")
+    _lib.check(_lib.lib().spb_dense_desc(nhwc.data_ptr(), B, Hc, Wc, 256, 8, dense.data_ptr(),
+                                         torch.cuda.current_stream().cuda_stream), "dense_desc")
+    assert torch.isfinite(dense).all() and (dense.cpu() - ref).abs().max().item() < 2e-6
