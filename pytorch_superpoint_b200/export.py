@@ -184,13 +184,50 @@ def export_detector_homoAdapt_b200(config, output_dir, args=None, loader=None, n
         ckpt = torch.load(path, map_location=lambda storage, loc: storage)
         net = SuperPointNet_b200()
         net.load_state_dict(ckpt["model_state_dict"] if path[-4:] == ".tar" else ckpt)
-    if config["model"].get("subpixel", {}).get("enable", False):
-        from .subpixel import soft_argmax_points
+    from .subpixel import soft_argmax_points
     exporter = HAExporter(net, conf_thresh, nms_dist, top_k)
     rank, world = world_info()
-    count = 0
-    count_seen = 0
+    subpixel = bool(config["model"].get("subpixel", {}).get("enable", False))
+    batch_images = max(1, int(config["model"].get("b200_batch_images", 8)))  # images per GPU step (ours, optional)
     seed0 = int(config.get("seed", 0)) * 1000003  # every rank draws the same matrices for image k (shards must agree)
+    from concurrent.futures import ThreadPoolExecutor
+    writers = ThreadPoolExecutor(max_workers=2)  # np.savez_compressed (zlib) off the submitting thread
+    writes, pending, batch = [], [], []
+    count = 0
+    seen = 0
+
+    def collect_oldest():
+        nonlocal count
+        ticket, metas = pending.pop(0)
+        for b, pts in enumerate(exporter.collect(ticket)):
+            if pts is None:  # another rank owns this image
+                continue
+            target, scene = metas[b]
+            if subpixel:
+                pts = soft_argmax_points(ticket["heat"][b], pts.T, 5).T
+            if scene is not None:
+                os.makedirs(os.path.join(save_output, scene), exist_ok=True)
+            writes.append(writers.submit(np.savez_compressed, target, pts=pts))
+            count += 1
+
+    def flush():
+        """Submit the accumulated images as ONE batch (H2D on the copy stream, kernels, NMS on the side stream) and
+        collect the batch before it: the host work of batch i overlaps the GPU work of batch i+1."""
+        nonlocal seen
+        if not batch:
+            return
+        imgs = [m[0] for m in batch]
+        if all(m[1] is not None for m in batch):
+            mu, mf = torch.stack([m[1] for m in batch]), torch.stack([m[2] for m in batch])
+        else:  # drawn on the GPU, one launch per batch (the host sampler costs ~2 s per 100, like the reference's)
+            mu, mf = sample_ha_homographies_device(num, len(batch), seed=seed0 + seen,
+                                                   params=ha["homographies"]["params"])
+        seen += len(batch)
+        pending.append((exporter.submit(imgs, mu, mf), [(m[3], m[4]) for m in batch]))
+        batch.clear()
+        while len(pending) > 1:
+            collect_oldest()
+
     for sample in loader:
         name = sample["name"][0] if not isinstance(sample["name"], str) else sample["name"]
         target = os.path.join(save_output, "{}.npz".format(name))
@@ -198,21 +235,26 @@ def export_detector_homoAdapt_b200(config, output_dir, args=None, loader=None, n
             continue
         img = sample["image_2D"] if "image_2D" in sample else sample["image"]
         img = torch.as_tensor(np.asarray(img), dtype=torch.float32).squeeze()
+        if img.dim() != 2:
+            raise ValueError(f"expected one gray image per sample, got {tuple(img.shape)}")
+        if batch and batch[0][0].shape != img.shape:
+            flush()
+        mu = mf = None
         if "homographies" in sample:
             mu = torch.as_tensor(np.asarray(sample["homographies"]), dtype=torch.float32).reshape(-1, 3, 3)
             mf = torch.as_tensor(np.asarray(sample["inv_homographies"]), dtype=torch.float32).reshape(-1, 3, 3)
-        else:  # drawn on the GPU (one launch; the host sampler costs ~2 s per 100 homographies, like the reference's)
-            h, inv = sample_ha_homographies_device(num, 1, seed=seed0 + count_seen, params=ha["homographies"]["params"])
-            mu, mf = h[0], inv[0]
-        count_seen += 1
-        pts = exporter.export_image(img, mu, mf)
-        if pts is None:
-            continue
-        if config["model"].get("subpixel", {}).get("enable", False):
-            heat = exporter.last_heat(1, img.shape[-2], img.shape[-1])[0]
-            pts = soft_argmax_points(heat, pts.T, 5).T
-        if "scene_name" in sample:
-            os.makedirs(os.path.join(save_output, sample["scene_name"][0]), exist_ok=True)
-        np.savez_compressed(target, pts=pts)
-        count += 1
+        scene = sample["scene_name"][0] if "scene_name" in sample else None
+        batch.append((img.pin_memory() if not img.is_pinned() else img, mu, mf, target, scene))
+        if len(batch) == batch_images:
+            flush()
+    flush()
+    while pending:
+        collect_oldest()
+    for w in writes:
+        w.result()  # re-raise I/O errors like the reference's synchronous savez would
+    writers.shutdown()
+    if world > 1:  # count over all ranks (each image is written by exactly one)
+        t = torch.tensor([count], device=exporter.device)
+        dist.all_reduce(t, group=exporter.group)
+        count = int(t.item())
     return count

@@ -284,3 +284,39 @@ def test_dense_desc_vs_torch(B, Hc, Wc):
     _lib.check(_lib.lib().spb_dense_desc(nhwc.data_ptr(), B, Hc, Wc, 256, 8, dense.data_ptr(),
                                          torch.cuda.current_stream().cuda_stream), "dense_desc")
     assert torch.isfinite(dense).all() and (dense.cpu() - ref).abs().max().item() < 2e-6
+
+
+def test_export_entry_batches_and_mixed_shapes(tmp_path):
+    """The .npz entry point batches images (b200_batch_images), flushes on a shape change and on the tail, pipelines
+    submit/collect and writes one file per image; key-points agree with the one-image-at-a-time export."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from pytorch_superpoint_b200 import SuperPointNet_b200, make_ha_homographies
+    from pytorch_superpoint_b200.export import HAExporter, export_detector_homoAdapt_b200
+    net = SuperPointNet_b200()
+    net.load_state_dict(O.synthetic_state_dict("gauss2", seed=2))
+    rng = np.random.RandomState(8)
+    N = 5
+    shapes = [(64, 96)] * 6 + [(48, 64)] * 3 + [(64, 96)] * 2
+    samples = []
+    for i, (H, W) in enumerate(shapes):
+        img = np.full((H, W), 0.3, np.float32)
+        for _ in range(6):
+            x0, y0 = rng.randint(0, W - 12), rng.randint(0, H - 12)
+            img[y0:y0 + rng.randint(6, 24), x0:x0 + rng.randint(6, 30)] = rng.uniform(0, 1)
+        mu, mf = make_ha_homographies(N, seed=100 + i)
+        samples.append({"image_2D": torch.from_numpy(img)[None, None], "name": [f"m{i}"],
+                        "homographies": torch.from_numpy(mu)[None], "inv_homographies": torch.from_numpy(mf)[None]})
+    cfg = {"model": {"nms": 4, "top_k": 80, "detection_threshold": 0.015, "subpixel": {"enable": False},
+                     "b200_batch_images": 4},
+           "data": {"export_folder": "val", "dataset": "Coco",
+                    "homography_adaptation": {"num": N, "homographies": {"params": {}}}}}
+    assert export_detector_homoAdapt_b200(cfg, str(tmp_path), loader=samples, net=net) == len(samples)
+    single = HAExporter(net, 0.015, 4, 80)
+    for i in (0, 5, 7, 10):
+        got = np.load(os.path.join(str(tmp_path), "predictions", "val", f"m{i}.npz"))["pts"]
+        ref = single.export_image(samples[i]["image_2D"][0, 0], samples[i]["homographies"][0],
+                                  samples[i]["inv_homographies"][0])
+        a = {(int(x), int(y)) for x, y, _ in got}
+        b = {(int(x), int(y)) for x, y, _ in ref}
+        assert got.dtype == np.float64 and len(a & b) / max(len(a | b), 1) > 0.95
