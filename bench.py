@@ -315,6 +315,27 @@ def run_b200(args):
             "gpu_launches": launches, "roofline": roofline, "stage_ms_per_step": stage_ms,
             "profiled_ms_per_step": round(ms_prof / prof_steps, 4), "clocks": clk.summary()}
 
+    # ---- second half of the BASELINE metric: single-frame extraction ms/image (configs[2]: batch 64, top-k 1000,
+    # detector + descriptor heads, NMS, sparse descriptors) next to the CPU oracle on one image (configs[0]) -----
+    if rank == 0 and world == 1:
+        from pytorch_superpoint_b200.frontend import SuperPointFrontend_b200
+        fe = SuperPointFrontend_b200({"model": {"subpixel": {"enable": False}}}, "", NMS, THR, 0.7, load=False,
+                                     device=str(dev))
+        fe.net = net
+        xb = torch.from_numpy(structured_images(64, seed=5)[:, None]).to(dev)
+        for _ in range(3):
+            fe.extract_batch(xb, top_k=1000)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            p_, c_, d_ = fe.extract_batch(xb, top_k=1000)
+        e1.record()
+        torch.cuda.synchronize()
+        line["extract"] = {"ms_per_image": round(e0.elapsed_time(e1) / 10 / 64, 5), "batch": 64, "top_k": 1000,
+                           "workload": "configs[2]: key-point + descriptor extraction, batch 64 at 240x320, device resident",
+                           "mean_keypoints": round(float(c_.float().mean().item()), 1)}
+
     if rank == 0 and world == 1 and not args.no_cpu:
         from oracle import oracle as O  # the CPU baseline leg: the one place this arm touches oracle/
         cores = os.cpu_count() or 1
@@ -333,6 +354,13 @@ def run_b200(args):
         a = {(int(x), int(y)) for x, y, _ in pts_gpu}
         b = {(int(x), int(y)) for x, y, _ in pts_cpu}
         line["keypoint_jaccard_vs_cpu_fp32"] = round(len(a & b) / max(len(a | b), 1), 4)
+        # configs[0]: the same single-frame extraction on the host cores (CPU oracle, one image)
+        x1 = torch.from_numpy(structured_images(1, seed=5)[:, None])
+        t0 = time.perf_counter()
+        semi_c, desc_c = O.net_forward(params, x1)
+        pts_c = O.get_pts_from_heatmap(O.flatten_detection(semi_c.numpy())[0], THR, NMS)[:, :1000]
+        O.sample_desc_from_points(desc_c.numpy(), pts_c)
+        line["extract"]["cpu_ms_per_image"] = round((time.perf_counter() - t0) * 1e3, 2)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

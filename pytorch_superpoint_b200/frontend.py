@@ -161,6 +161,38 @@ class SuperPointFrontend_b200(object):
         return pts, pts_desc, dense, heat
 
 
+def _extract_batch(self, inp, top_k=0):
+    """Batched single-frame extraction (export.py:127-145 per image, BASELINE configs[0]/[2]) with everything left on
+    the device: inp [B,1,H,W] -> (pts [B,cap,3] fp32 rows (x, y, conf) sorted by confidence, counts [B] int32,
+    desc [B,cap,256] fp32 unit-norm descriptors sampled at the key-points).  No host synchronisation."""
+    if self.net is None:
+        raise RuntimeError("no network loaded")
+    dev = torch.device(self.device) if torch.device(self.device).type == "cuda" else torch.device("cuda")
+    inp = inp.to(dev)
+    B, H, W = inp.shape[0], inp.shape[2], inp.shape[3]
+    from . import _lib
+    with torch.no_grad():
+        semi, desc = self.net.forward_nhwc(inp, want_desc=True)
+    heat = torch.empty((B, H, W), device=dev, dtype=torch.float32)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().spb_flatten_detection(semi.data_ptr(), 65, heat.data_ptr(), B, H // 8, W // 8,
+                                                    torch.cuda.current_stream().cuda_stream), "flatten_detection")
+    pts, counts, _ = ops.get_pts_from_heatmap_device(heat, self.conf_thresh, self.nms_dist, self.border_remove, top_k)
+    out = torch.zeros((B, pts.shape[1], desc.shape[-1]), device=dev, dtype=torch.float32)
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        st = torch.cuda.current_stream().cuda_stream
+        for b in range(B):
+            _lib.check(L.spb_sample_desc_from_points(desc[b].data_ptr(), 1, pts[b].data_ptr(), counts[b:b + 1].data_ptr(),
+                                                     pts.shape[1], H // self.cell, W // self.cell, desc.shape[-1],
+                                                     self.cell, out[b].data_ptr(), st), "sample_desc_from_points")
+    self.heatmap = heat[:, None]
+    return pts, counts, out
+
+
+SuperPointFrontend_b200.extract_batch = _extract_batch
+
+
 class PointTracker_b200(object):
     """The matching half of ``models/model_wrap.py:411-583 PointTracker``: ``nn_match_two_way`` on the GPU
     (same arguments, float64 ``[3,L]`` result, ``mscores`` attribute, ValueError on a negative threshold)."""

@@ -320,3 +320,21 @@ def test_export_entry_batches_and_mixed_shapes(tmp_path):
         a = {(int(x), int(y)) for x, y, _ in got}
         b = {(int(x), int(y)) for x, y, _ in ref}
         assert got.dtype == np.float64 and len(a & b) / max(len(a | b), 1) > 0.95
+
+
+def test_extract_batch_matches_per_image_path():
+    """Device-resident batched extraction == the reference-facing per-image functions on the same heat-map."""
+    fe = _fe(device="cuda")
+    from pytorch_superpoint_b200 import SuperPointNet_b200
+    fe.net = SuperPointNet_b200()
+    fe.net.load_state_dict(O.synthetic_state_dict("gauss2", seed=4))
+    x = torch.rand(3, 1, 64, 96, generator=torch.Generator().manual_seed(2)).cuda()
+    pts, counts, desc = fe.extract_batch(x, top_k=50)
+    assert tuple(pts.shape) == (3, 50, 3) and tuple(desc.shape) == (3, 50, 256)
+    semi, dmap = fe.net.forward_nhwc(x)
+    for b in range(3):
+        k = int(counts[b])
+        ref = fe.getPtsFromHeatmap(fe.heatmap[b, 0])[:, :50]
+        assert k == ref.shape[1] and np.array_equal(pts[b, :k].cpu().numpy().astype(np.float64).T, ref)
+        d = fe.sample_desc_from_points(dmap[b:b + 1].permute(0, 3, 1, 2).contiguous(), ref)
+        assert np.abs(desc[b, :k].cpu().numpy().T - d).max() < 1e-6
