@@ -101,17 +101,20 @@ class SuperPointNet_process_b200(object):
     def batch_extract_features(self, desc, heatmap_nms_batch, residual):
         """desc [B,D,Hc,Wc], mask [B,1,H,W], residual [N,2] in mask.nonzero() order -> dict of
         'pts_int' [B,M,2] (x, y), 'pts_offset' [B,M,2], 'pts_desc' [B,M,D] with M = out_num_points."""
-        batch_size = heatmap_nms_batch.shape[0]
+        mask = torch.as_tensor(heatmap_nms_batch)
+        B = mask.shape[0]
+        idx = mask.nonzero()                                   # [N,4] (b, 0, y, x), sorted by image then row-major
+        per_image = torch.bincount(idx[:, 0], minlength=B).tolist()
+        xy = idx[:, [3, 2]].float()                            # integer key-points as (x, y)
         pts_int, pts_offset, pts_desc = [], [], []
-        pts_idx = torch.as_tensor(heatmap_nms_batch).nonzero()
-        for i in range(batch_size):
-            mask_b = pts_idx[:, 0] == i
-            pts_int_b = pts_idx[mask_b][:, 2:].float()[:, [1, 0]]
-            res_b = residual[mask_b]
-            pts_desc_b = self.sample_desc_from_points(desc[i].unsqueeze(0), pts_int_b + res_b).squeeze(0)
-            choice = torch.tensor(crop_or_pad_choice(pts_int_b.shape[0], self.out_num_points, shuffle=True))
-            pts_int.append(pts_int_b[choice])
-            pts_offset.append(res_b[choice])
-            pts_desc.append(pts_desc_b[choice])
+        start = 0
+        for b, n_b in enumerate(per_image):
+            xy_b, res_b = xy[start:start + n_b], residual[start:start + n_b]
+            start += n_b
+            d_b = self.sample_desc_from_points(desc[b:b + 1], xy_b + res_b)[0]      # descriptors at the refined points
+            pick = torch.as_tensor(crop_or_pad_choice(n_b, self.out_num_points, shuffle=True), device=xy_b.device)
+            pts_int.append(xy_b[pick])
+            pts_offset.append(res_b[pick])
+            pts_desc.append(d_b[pick])
         return {"pts_int": torch.stack(pts_int, dim=0), "pts_offset": torch.stack(pts_offset, dim=0),
                 "pts_desc": torch.stack(pts_desc, dim=0)}
