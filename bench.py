@@ -188,7 +188,7 @@ def run_b200(args):
     # the timed region.  End-to-end arm: drawn afresh on the GPU inside every step (sampler.cu; all
     # ranks use the same counter-based seed, so the shards agree on the matrices).
     from pytorch_superpoint_b200.homographies import sample_ha_homographies_device
-    imgs_host = [torch.from_numpy(imgs_np[b]).pin_memory() for b in range(B)]
+    imgs_host = torch.from_numpy(imgs_np).pin_memory()  # one collated, pinned [B,H,W] batch (DataLoader style)
     imgs_dev = torch.from_numpy(imgs_np).to(dev)
     mu_dev, mf_dev = sample_ha_homographies_device(NVIEWS, B, seed=0, device=dev)
     from pytorch_superpoint_b200 import ops

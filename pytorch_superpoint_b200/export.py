@@ -114,8 +114,9 @@ class HAExporter:
         """Host images in (pinned for true async copies): H2D + submit_resident.  Returns a ticket for collect().
         The copies run on a copy stream into one of two device image buffers, so the H2D of batch i+1 overlaps the
         kernels of batch i (the main stream only waits for its own batch's copy event)."""
-        B = len(imgs_host)
-        H, W = imgs_host[0].shape[-2:]
+        collated = torch.is_tensor(imgs_host)  # a DataLoader-style [B,H,W] / [B,1,H,W] batch: ONE copy
+        B = imgs_host.shape[0] if collated else len(imgs_host)
+        H, W = imgs_host.shape[-2:] if collated else imgs_host[0].shape[-2:]
         buf = self._buffers(B, H, W)
         with torch.cuda.device(self.device):
             j = buf["kin"] & 1
@@ -125,8 +126,11 @@ class HAExporter:
             if buf["img_free"][j] is not None:
                 self._copy.wait_event(buf["img_free"][j])  # the batch that last read this buffer has consumed it
             with torch.cuda.stream(self._copy):
-                for b in range(B):
-                    img[b].copy_(imgs_host[b].reshape(H, W), non_blocking=True)
+                if collated:
+                    img.copy_(imgs_host.reshape(B, H, W), non_blocking=True)
+                else:
+                    for b in range(B):
+                        img[b].copy_(imgs_host[b].reshape(H, W), non_blocking=True)
                 mu = mats_unwarp.to(self.device, torch.float32, non_blocking=True)
                 mf = mats_fwd.to(self.device, torch.float32, non_blocking=True)
                 copied = torch.cuda.Event()
