@@ -31,6 +31,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "r"(bar), "r"(parity)
         : "memory");
     if (ok) return;
+    // (a __nanosleep here was measured: 20 / 100 ns back-off costs 1.5 % of throughput, no power-cap relief)
     if (clock64() - t0 > 4000000000LL) {
       printf("spb200 conv_tc: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x,
              threadIdx.x, bar, parity);
