@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(kS3Threads, 1) conv_s3_kernel(const __grid_con
         tma_store_commit();
       }
     }
-    if (store_thread) tma_store_wait_read<0>();
+    if (store_thread) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();

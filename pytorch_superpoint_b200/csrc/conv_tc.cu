@@ -473,7 +473,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) conv_tc_kernel(const __grid_con
      }  // tiles of the stage
       if (++as == 2) { as = 0; pacc ^= 1; }
     }
-    if ((C::TMA_OUT || C::OUT == 3) && lane == 0) tma_store_wait_read<0>();
+    if ((C::TMA_OUT || C::OUT == 3) && lane == 0) tma_store_wait_all();
   }
 
   tc_fence_before();
@@ -622,7 +622,7 @@ __global__ void __launch_bounds__(160, 4) conv1a_tc_kernel(const __grid_constant
         tma_store_commit();
       }
     }
-    if (threadIdx.x == 0) tma_store_wait_read<0>();
+    if (threadIdx.x == 0) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();
@@ -959,7 +959,7 @@ __global__ void __launch_bounds__(576, 1) conv1_fused_kernel(const __grid_consta
       }
       if (a.dbg && blockIdx.x == 0 && it < 64 && threadIdx.x == 64) a.dbg[it * 16 + 12] = clock64();
     }
-    if (issuer) tma_store_wait_read<0>();
+    if (issuer) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();
