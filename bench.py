@@ -280,9 +280,11 @@ def run_b200(args):
     names = ["conv1a", "conv1b", "conv2a", "conv2b", "conv3a", "conv3b", "conv4a", "conv4b", "convPa", "convPb",
              "convDa", "convDb", "warp", "aggregate"]
     stage_ms = {names[i]: round(st_ms[i] / prof_steps, 4) for i in range(14) if st_n[i]}
-    from pytorch_superpoint_b200.sharding import shard_bounds
+    from pytorch_superpoint_b200.sharding import balanced_view_plan, shard_bounds
     lo, hi = shard_bounds(NVIEWS, rank, world)
-    views_local = hi - lo
+    views_local = hi - lo  # views per image on this rank ...
+    if world > 1 and NVIEWS % world and B >= world and -(-NVIEWS // world) * B <= 800:
+        views_local = len(balanced_view_plan(B, NVIEWS, rank, world)[0]) / B  # ... averaged over the rotated shares
     peak_tf, peak_hbm, peak_src = peaks()
     # stage 1 = conv1_fused_kernel: conv1a (1->64) + conv1b (64->64) + pool in one launch
     k_launches = st_n[1]
@@ -307,7 +309,8 @@ def run_b200(args):
             "config": {"workload": WORKLOAD, "images_per_step": B, "homographies": NVIEWS,
                        "homography_sets": "one set of 100 per image (datasets/Coco.py:262-276); resident arm: pre-sampled; "
                                           "e2e arm: drawn on the GPU inside every step",
-                       "parallelism": f"homography-sharded x{world}, 1 NCCL all-reduce of [B,2,H,W] per step",
+                       "parallelism": f"homography-sharded x{world} (uneven shares rotated over the images of the batch: "
+                                      f"{B * NVIEWS // world} views per rank and step), 1 NCCL all-reduce of [B,2,H,W] per step",
                        "l2": "per-image activation working set ~1.3 GB streams through the 126 MB L2 every step "
                              "(inputs larger than L2; no explicit flush)", "ha_chunk": args.chunk},
             "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

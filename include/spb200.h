@@ -188,6 +188,16 @@ int spb_ha_heatmap_sums_batch(spb_net* net, const float* imgs, const float* mats
                               int shared_mats, int B, int N, int H, int W, float* sums, int accumulate, void* ws,
                               size_t ws_bytes, void* stream);
 
+/* Balanced homography sharding (a rank's share of 100 views over 8 ranks is 12 or 13 per image; rotating the
+ * larger shares over the images of a batch gives every rank the same number of views per step): V views as a flat
+ * list, view v belongs to image view_image[v] (device int[V], grouped by image in ascending order) and image b owns
+ * the views [view_offsets[b], view_offsets[b+1]) (device int[B+1]); mats_* [V,3,3] in view order.  One pass, so V is
+ * bounded by the workspace the caller provides. */
+size_t spb_ha_workspace_bytes_ragged(int B, int V, int max_views_per_image, int H, int W);
+int spb_ha_heatmap_sums_ragged(spb_net* net, const float* imgs, const float* mats_unwarp, const float* mats_fwd,
+                               const int* view_image, const int* view_offsets, int B, int V, int max_views_per_image,
+                               int H, int W, float* sums, int accumulate, void* ws, size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

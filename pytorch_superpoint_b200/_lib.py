@@ -54,6 +54,8 @@ PROTOTYPES = {
     "spb_ha_workspace_bytes": (_z, [_i, _i, _i]),
     "spb_ha_heatmap_sums": (_i, [_p, _p, _p, _p, _i, _i, _i, _p, _i, _p, _z, _p]),
     "spb_ha_workspace_bytes_batch": (_z, [_p, _i, _i, _i, _i]),
+    "spb_ha_workspace_bytes_ragged": (_z, [_i, _i, _i, _i, _i]),
+    "spb_ha_heatmap_sums_ragged": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _i, _p, _z, _p]),
     "spb_ha_heatmap_sums_batch": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _i, _p, _z, _p]),
 }
 # debug knobs exported by the library but not part of the public header

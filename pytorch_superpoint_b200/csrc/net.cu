@@ -359,7 +359,7 @@ int spb_ha_heatmap_sums_batch(spb_net* h, const float* imgs, const float* mats_u
       {
         StageTimer tm(net, 12, st);
         rc = warp_with_mask_bits(imgs + (long long)b0 * H * W, mats_fwd + moff, warped, bits, bg * nn, nn, shared_mats,
-                                 H, W, st);
+                                 nullptr, H, W, st);
       }
       if (rc != SPB_OK) return rc;
       // the detector head writes softmax probabilities directly (tcgen05 epilogue); the validation path goes
@@ -375,6 +375,51 @@ int spb_ha_heatmap_sums_batch(spb_net* h, const float* imgs, const float* mats_u
     }
   }
   return SPB_OK;
+}
+
+// Balanced homography sharding: a flat list of V views with a different number of views per image.
+size_t spb_ha_workspace_bytes_ragged(int B, int V, int max_views_per_image, int H, int W) {
+  if (B < 1 || V < 1 || max_views_per_image < 1 || H < 8 || W < 8) return 0;
+  HaLayout L = ha_layout(1, V, H, W);
+  return L.total + align_up(aggregate_probs_workspace(B, max_views_per_image, H, W), 1024);
+}
+
+int spb_ha_heatmap_sums_ragged(spb_net* h, const float* imgs, const float* mats_unwarp, const float* mats_fwd,
+                               const int* view_image, const int* view_offsets, int B, int V, int max_views_per_image,
+                               int H, int W, float* sums, int accumulate, void* ws, size_t ws_bytes, void* stream) {
+  SPB_CHECK_ARG(h && imgs && mats_unwarp && mats_fwd && view_image && view_offsets && sums && ws);
+  SPB_CHECK_ARG(B >= 1 && V >= 1 && max_views_per_image >= 1 && H >= 8 && W >= 8 && H % 8 == 0 && W % 8 == 0);
+  Net* net = reinterpret_cast<Net*>(h);
+  if (net->impl != SPB_IMPL_TCGEN05) {
+    set_error("spb_ha_heatmap_sums_ragged: tcgen05 implementation only");
+    return SPB_EINVAL;
+  }
+  if (ws_bytes < spb_ha_workspace_bytes_ragged(B, V, max_views_per_image, H, W)) {
+    set_error("spb_ha_heatmap_sums_ragged: workspace %zu < %zu bytes", ws_bytes,
+              spb_ha_workspace_bytes_ragged(B, V, max_views_per_image, H, W));
+    return SPB_ENOMEM;
+  }
+  const HaLayout L = ha_layout(1, V, H, W);
+  char* base = static_cast<char*>(align_ptr(ws));
+  float* warped = reinterpret_cast<float*>(base + L.warp);
+  uint8_t* bits = reinterpret_cast<uint8_t*>(base + L.bits);
+  float* probs = reinterpret_cast<float*>(base + L.probs);
+  char* agg_ws = base + L.total - 1024;  // the aggregate's partial sums live behind the single-image layout
+  cudaStream_t st = as_stream(stream);
+  int rc;
+  {
+    StageTimer tm(net, 12, st);
+    rc = warp_with_mask_bits(imgs, mats_fwd, warped, bits, V, 1, 0, view_image, H, W, st);
+  }
+  if (rc != SPB_OK) return rc;
+  rc = forward(net, warped, V, H, W, nullptr, probs, nullptr, base + L.net, st);
+  if (rc != SPB_OK) return rc;
+  {
+    StageTimer tm(net, 13, st);
+    rc = aggregate_probs(probs, bits, mats_unwarp, 0, B, max_views_per_image, H, W, sums, accumulate, agg_ws, st,
+                         view_offsets);
+  }
+  return rc;
 }
 
 int spb_ha_heatmap_sums(spb_net* h, const float* img, const float* mats_unwarp, const float* mats_fwd, int N, int H,

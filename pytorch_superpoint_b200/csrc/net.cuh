@@ -41,10 +41,10 @@ int l2norm_rows(float* d, long long rows, int C, cudaStream_t st);
 
 // warp.cu / heat.cu pieces used by the fused HA path
 int warp_with_mask_bits(const float* img, const float* mats, float* out, uint8_t* bits, int N, int vpi,
-                        int shared_mats, int H, int W, cudaStream_t st);
+                        int shared_mats, const int* view_img, int H, int W, cudaStream_t st);
 size_t aggregate_probs_workspace(int B, int N, int H, int W);
 int aggregate_probs(const float* probs, const uint8_t* bits, const float* mats_unwarp, int shared_mats, int B, int N,
-                    int H, int W, float* sums, int accumulate, void* ws, cudaStream_t st);
+                    int H, int W, float* sums, int accumulate, void* ws, cudaStream_t st, const int* offs = nullptr);
 
 // conv_tc.cu (tcgen05 / TMEM / TMA)
 int conv1a_tc(const LayerDev& L, const float* x, __nv_bfloat16* out, int B, int H, int W, cudaStream_t st);

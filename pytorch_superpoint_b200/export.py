@@ -18,7 +18,7 @@ import torch.distributed as dist
 from . import ops
 from .homographies import make_ha_homographies, sample_ha_homographies_device  # noqa: F401
 from .net import SuperPointNet_b200
-from .sharding import owner_of_image, shard_bounds, world_info
+from .sharding import balanced_view_plan, owner_of_image, shard_bounds, world_info
 
 __all__ = ["HAExporter", "export_detector_homoAdapt_b200"]
 
@@ -37,6 +37,7 @@ class HAExporter:
         self.group = group
         self.chunk = chunk
         self._bufs = {}
+        self._plan_key, self._plan = None, None
 
     def _buffers(self, B, H, W):
         key = (B, H, W)
@@ -66,7 +67,22 @@ class HAExporter:
         N = mats_unwarp.shape[-3]
         lo, hi = shard_bounds(N, rank, world)
         sums = buf["sums"]
-        if hi > lo:
+        if world > 1 and N % world and B >= world and -(-N // world) * B <= 800:
+            # uneven shares (100 views over 8 ranks = 13 or 12 per image): rotate them over the images of the batch so
+            # that every rank processes the same number of views per step (sharding.balanced_view_plan)
+            key = (B, N, rank, world)
+            if self._plan_key != key:
+                sel, vi, vo, most = balanced_view_plan(B, N, rank, world)
+                self._plan_key, self._plan = key, (sel.to(self.device), vi.to(self.device), vo.to(self.device), most)
+            sel, vi, vo, most = self._plan
+            mats_unwarp = mats_unwarp.to(self.device, torch.float32)
+            mats_fwd = mats_fwd.to(self.device, torch.float32)
+            if per_image:
+                mu, mf = mats_unwarp.reshape(B * N, 3, 3)[sel], mats_fwd.reshape(B * N, 3, 3)[sel]
+            else:
+                mu, mf = mats_unwarp[sel % N], mats_fwd[sel % N]
+            self.net.ha_heatmap_sums_ragged(imgs_dev, mu, mf, vi, vo, most, sums=sums)
+        elif hi > lo:
             mu = mats_unwarp[:, lo:hi] if per_image else mats_unwarp[lo:hi]
             mf = mats_fwd[:, lo:hi] if per_image else mats_fwd[lo:hi]
             self.net.ha_heatmap_sums_batch(imgs_dev, mu, mf, sums=sums, chunk=self.chunk)

@@ -183,6 +183,35 @@ class SuperPointNet_b200(nn.Module):
                                          None if sums is None else sums.reshape(1, 2, H, W), accumulate, chunk)
         return out[0]
 
+    def ha_heatmap_sums_ragged(self, imgs, mats_unwarp, mats_fwd, view_image, view_offsets, max_views, sums=None,
+                               accumulate=False):
+        """Balanced homography sharding: imgs [B,H,W]; V views as a flat list -- mats [V,3,3], ``view_image`` int32 [V]
+        (image of every view, grouped by image), ``view_offsets`` int32 [B+1], ``max_views`` = the largest per-image
+        count -> sums [B,2,H,W].  One pass over all V views."""
+        dev = imgs.device
+        B, H, W = imgs.shape
+        mu = mats_unwarp.to(dev, torch.float32).contiguous()
+        mf = mats_fwd.to(dev, torch.float32).contiguous()
+        V = mu.shape[0]
+        vi = view_image.to(dev, torch.int32).contiguous()
+        vo = view_offsets.to(dev, torch.int32).contiguous()
+        if vi.numel() != V or vo.numel() != B + 1:
+            raise ValueError("view_image must be [V] and view_offsets [B+1]")
+        h = self.handle(dev)
+        L = _lib.lib()
+        nbytes = L.spb_ha_workspace_bytes_ragged(B, V, int(max_views), H, W)
+        ws = self._workspace(nbytes, dev)
+        if sums is None:
+            sums = torch.empty((B, 2, H, W), device=dev, dtype=torch.float32)
+            accumulate = False
+        assert sums.is_contiguous()
+        with torch.cuda.device(dev):
+            _lib.check(L.spb_ha_heatmap_sums_ragged(h, imgs.contiguous().data_ptr(), mu.data_ptr(), mf.data_ptr(),
+                                                    vi.data_ptr(), vo.data_ptr(), B, V, int(max_views), H, W,
+                                                    sums.data_ptr(), int(bool(accumulate)), ws.data_ptr(), ws.numel(),
+                                                    torch.cuda.current_stream().cuda_stream), "ha_heatmap_sums_ragged")
+        return sums
+
     def ha_heatmap_sums_batch(self, imgs, mats_unwarp, mats_fwd, sums=None, accumulate=False, chunk: int = 0):
         """imgs [B,H,W] cuda fp32; mats [N,3,3] shared by the batch or [B,N,3,3] -> sums [B,2,H,W].
         All B*N views go through the kernels in passes of at most ``chunk`` views (0 = library default)."""

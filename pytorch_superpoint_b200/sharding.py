@@ -15,7 +15,7 @@ from typing import Callable, Tuple
 import torch
 import torch.distributed as dist
 
-__all__ = ["shard_bounds", "owner_of_image", "sharded_heatmap_sums", "world_info"]
+__all__ = ["shard_bounds", "balanced_view_plan", "owner_of_image", "sharded_heatmap_sums", "world_info"]
 
 
 def world_info(group=None) -> Tuple[int, int]:
@@ -32,6 +32,28 @@ def shard_bounds(num_views: int, rank: int, world: int) -> Tuple[int, int]:
     base, extra = divmod(num_views, world)
     lo = rank * base + min(rank, extra)
     return lo, lo + base + (1 if rank < extra else 0)
+
+
+def balanced_view_plan(num_images: int, num_views: int, rank: int, world: int):
+    """Homography sharding balanced over a BATCH: image b gives rank r the block ``shard_bounds(N, (r + b) % world)``,
+    so the larger shares (13 of 100 views over 8 ranks, against 12) rotate over the images and every rank ends up with
+    the same number of views per step when ``num_images % world == 0`` (plain per-image blocks leave the 13-view ranks
+    4 % more work than the average, and the step runs at their pace).  Every (image, view) pair still belongs to
+    exactly one rank and every image is spread over all ranks.
+
+    Returns ``(select, view_image, view_offsets, max_views)``: ``select`` indexes the image-major flat list of
+    ``num_images * num_views`` (image, view) pairs, ``view_image[v]`` is the image of the v-th selected view,
+    image b owns ``[view_offsets[b], view_offsets[b+1])`` (int64 / int32 / int32 tensors on the CPU)."""
+    select, view_image, offsets = [], [], [0]
+    most = 0
+    for b in range(num_images):
+        lo, hi = shard_bounds(num_views, (rank + b) % world, world)
+        select.extend(range(b * num_views + lo, b * num_views + hi))
+        view_image.extend([b] * (hi - lo))
+        offsets.append(offsets[-1] + hi - lo)
+        most = max(most, hi - lo)
+    return (torch.tensor(select, dtype=torch.int64), torch.tensor(view_image, dtype=torch.int32),
+            torch.tensor(offsets, dtype=torch.int32), most)
 
 
 def owner_of_image(b: int, world: int) -> int:

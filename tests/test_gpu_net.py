@@ -257,3 +257,27 @@ def test_ha_other_config_shapes_vs_oracle(H, W, N):
     assert np.isfinite(heat).all() and np.abs(heat - ref_heat).max() < 1e-2
     pts = getPtsFromHeatmap(torch.from_numpy(ref_heat).cuda(), 0.015, 4).T[:600]
     assert np.array_equal(pts, ref_pts)
+
+
+@pytest.mark.parametrize("B,H,W,N,world", [(4, 48, 64, 10, 4), (8, 64, 96, 13, 8), (3, 40, 24, 7, 3)])
+def test_ha_ragged_balanced_shards_sum_to_the_full_heatmap(B, H, W, N, world):
+    """Balanced homography sharding on one GPU: the `world` ragged partial sums (spb_ha_heatmap_sums_ragged with the
+    rotated per-image shares) add up to the unsharded sums, and each equals the per-image uniform calls on its views."""
+    from pytorch_superpoint_b200 import SuperPointNet_b200, sample_ha_homographies_device
+    from pytorch_superpoint_b200.sharding import balanced_view_plan
+    n = SuperPointNet_b200()
+    n.load_state_dict(O.synthetic_state_dict("gauss2", seed=2))
+    imgs = torch.rand(B, H, W, device="cuda", generator=torch.Generator("cuda").manual_seed(W))
+    mu, mf = sample_ha_homographies_device(N, B, seed=W)
+    full = n.ha_heatmap_sums_batch(imgs, mu, mf).clone()
+    total = torch.zeros_like(full)
+    for r in range(world):
+        sel, vi, vo, most = balanced_view_plan(B, N, r, world)
+        part = n.ha_heatmap_sums_ragged(imgs, mu.reshape(-1, 3, 3)[sel.cuda()], mf.reshape(-1, 3, 3)[sel.cuda()], vi, vo,
+                                        most).clone()
+        for b in range(B):
+            s = (sel[int(vo[b]):int(vo[b + 1])] % N).cuda()
+            ref = n.ha_heatmap_sums(imgs[b], mu[b][s], mf[b][s]).clone()
+            assert torch.allclose(part[b], ref, rtol=1e-5, atol=1e-6)
+        total += part
+    assert torch.allclose(total, full, rtol=1e-5, atol=1e-5)            # fp32 summation order differs only

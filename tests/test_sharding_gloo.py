@@ -77,3 +77,28 @@ def test_sharded_equals_unsharded(world):
         r = O.get_pts_from_heatmap(ref, 0.015, 4)
         sa, sr = {tuple(c[:2]) for c in a.T}, {tuple(c[:2]) for c in r.T}
         assert len(sa & sr) >= 0.97 * max(len(sa | sr), 1)  # threshold/tie flips from summation order only
+
+
+def test_balanced_view_plan_partitions_every_pair_once():
+    """Rotated shares: every (image, view) pair belongs to exactly one rank, every image is spread over all ranks, and
+    with B % world == 0 all ranks get the same number of views per step (100 views over 8 ranks: 400 each, not 416/384)."""
+    import torch
+    from pytorch_superpoint_b200.sharding import balanced_view_plan, shard_bounds
+    for B, N, world in [(32, 100, 8), (8, 100, 8), (6, 10, 4), (5, 7, 3), (16, 100, 3)]:
+        seen = torch.zeros(B * N, dtype=torch.int64)
+        totals = []
+        for r in range(world):
+            sel, vi, vo, most = balanced_view_plan(B, N, r, world)
+            seen[sel] += 1
+            totals.append(len(sel))
+            assert vo[0] == 0 and vo[-1] == len(sel) and len(vo) == B + 1 and len(vi) == len(sel)
+            for b in range(B):
+                lo, hi = int(vo[b]), int(vo[b + 1])
+                assert (vi[lo:hi] == b).all() and hi - lo <= most
+                assert (sel[lo:hi] // N == b).all() and hi > lo            # every rank touches every image
+                want = shard_bounds(N, (r + b) % world, world)
+                assert sel[lo] % N == want[0] and sel[hi - 1] % N == want[1] - 1
+        assert (seen == 1).all()
+        if B % world == 0:
+            assert max(totals) == min(totals) == B * N // world
+        assert max(totals) - min(totals) <= max(1, B % world)
