@@ -91,3 +91,33 @@ def test_synthetic_weights_match_oracle_generator():
     for layout in ("v1", "bnflat", "gauss2"):
         a, b = synthetic_state_dict(layout, 5), O.synthetic_state_dict(layout, 5)
         assert list(a) == list(b) and all(torch.equal(a[k], b[k]) for k in a)
+
+
+def test_cabi_argument_errors_without_a_gpu():
+    """Argument validation happens before any CUDA call: the error convention of the C ABI (negative code +
+    spb_last_error_string, never a throw) can be checked on the CPU box for the entry points added for the f rows."""
+    from pytorch_superpoint_b200 import _lib
+    L = _lib.lib()
+    buf = (ctypes.c_float * 64)()
+    ibuf = (ctypes.c_int * 8)()
+    p = lambda a: ctypes.cast(a, ctypes.c_void_p)  # noqa: E731
+    # models/model_wrap.py:455-456: a negative threshold is an error (ValueError in the reference)
+    rc = L.spb_nn_match_two_way(p(buf), 2, p(buf), 2, 4, -0.5, p(ibuf), p(ibuf), p(buf), p(ibuf), p(buf), 1024, None)
+    assert rc < 0 and b"nn_thresh" in L.spb_last_error_string()
+    assert L.spb_nn_match_workspace_bytes(10, 20) >= 30 * 8
+    # sampler: n_scales outside 1..16, patch_ratio outside (0, 1]
+    args = [0, 4, 2, 1, 1, 1, 1]
+    rc = L.spb_sample_ha_homographies(*args, 0, 25, 0.2, 0.2, 0.2, 0.85, 1.57, 1, 0.0, p(buf), p(buf), None, None)
+    assert rc < 0 and b"n_scales" in L.spb_last_error_string()
+    rc = L.spb_sample_ha_homographies(*args, 5, 25, 0.2, 0.2, 0.2, 1.5, 1.57, 1, 0.0, p(buf), p(buf), None, None)
+    assert rc < 0 and b"patch_ratio" in L.spb_last_error_string()
+    # dense descriptors: D must be a multiple of 8 up to 256
+    assert L.spb_dense_desc(p(buf), 1, 2, 2, 7, 8, p(buf), None) < 0
+    assert L.spb_roi_soft_argmax(None, 1, 8, 8, None, 3, p(buf), None, None) < 0
+    assert L.spb_sample_desc_from_points_ex(p(buf), 1, p(buf), 1, None, 4, 4, 4, 8, 8, 0, p(buf), None) < 0  # stride < 2
+    # ragged HA entry: a NULL network handle
+    assert L.spb_ha_heatmap_sums_ragged(None, p(buf), p(buf), p(buf), p(ibuf), p(ibuf), 1, 1, 1, 8, 8, p(buf), 0, p(buf),
+                                        64, None) < 0
+    assert L.spb_ha_workspace_bytes_ragged(0, 1, 1, 8, 8) == 0
+    with pytest.raises(RuntimeError, match="libspb200"):
+        _lib.check(-1, "demo")
