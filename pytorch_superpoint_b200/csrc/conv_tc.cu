@@ -660,6 +660,10 @@ struct Conv1FusedSmem {
 #ifndef SPB_C1A_TAP
 #define SPB_C1A_TAP 8  // conv1a of the issuer's next tile is issued behind this tap of conv1b
 #endif
+// Measured alternatives for getting conv1a's accumulator to stage 1 sooner (it waits ~750 cycles for it): issuing
+// conv1a behind tap 3 or 6 (-10..14 %), and a THIRD issuer warp that issues every conv1a the moment its im2col tile
+// is ready (+-0 %): the tensor pipe executes in issue order behind a queue of conv1b MMAs either way, and the block
+// already sits at 84 % of the shared-memory operand-read bound.
 struct Conv1FusedArgs {
   const __nv_bfloat16* w1a;     // [64][16]
   const float *bias1, *bias2;
