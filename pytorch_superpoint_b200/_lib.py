@@ -59,7 +59,7 @@ PROTOTYPES = {
     "spb_ha_heatmap_sums_batch": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _i, _p, _z, _p]),
 }
 # debug knobs exported by the library but not part of the public header
-_EXTRA = {"spb_conv_tc_set_halo": (_i, [_i]), "spb_conv_tc_set_fuse1": (_i, [_i]), "spb_conv_tc_set_s3": (_i, [_i]), "spb_conv_tc_set_pair": (_i, [_i]),
+_EXTRA = {"spb_conv_tc_set_halo": (_i, [_i]), "spb_conv_tc_set_fuse1": (_i, [_i]), "spb_conv_tc_set_s3": (_i, [_i]), "spb_conv_tc_set_pair": (_i, [_i]), "spb_conv_tc_set_cg2": (_i, [_i]),
           "spb_conv1_fused_set_probe": (_i, [_p])}
 
 IMPL_TCGEN05, IMPL_SIMT = 0, 1

@@ -1203,6 +1203,11 @@ int conv_tc(const LayerDev& L, const __nv_bfloat16* in, void* out, int B, int H,
   }
   if (L.w_s3 && conv_s3_enabled() && out_mode == 0)
     return conv_s3(L, in, static_cast<__nv_bfloat16*>(out), B, H, W, st);
+  if (g_halo_mode) {  // >= 128 output channels: CTA pairs (conv_tc2.cu) unless switched off
+    bool handled = false;
+    const int rc = conv_tc2(L, in, out, B, H, W, out_mode, st, &handled);
+    if (rc != SPB_OK || handled) return rc;
+  }
   const bool halo = g_halo_mode != 0;
 #define SPB_CONV(CIN, NPAD, KS, HALO, BRES, NA, NB, POOL, OUT) \
   launch<ConvCfg<CIN, NPAD, KS, HALO, BRES, NA, NB, POOL, OUT>>(L, in, out, B, H, W, out_mode, st)

@@ -58,6 +58,10 @@ int conv_tc_prepare(LayerDev& L);  // builds the weight tensor map after w_tc is
 int conv_tc(const LayerDev& L, const __nv_bfloat16* in, void* out, int B, int H, int W, int out_mode, cudaStream_t st);
 
 
+// conv_tc2.cu (CTA pairs, tcgen05.mma.cta_group::2, for the >= 128-output-channel 3x3 layers)
+int conv_tc2(const LayerDev& L, const __nv_bfloat16* in, void* out, int B, int H, int W, int out_mode, cudaStream_t st,
+             bool* handled);
+
 // conv_s3.cu (64 -> 64, N = 192 column-tap stacking)
 bool conv_s3_enabled();
 int conv_s3_prepare(LayerDev& L);  // after w_s3 is uploaded

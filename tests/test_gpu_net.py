@@ -123,6 +123,25 @@ def test_tile_pairs_equal_single_tiles(net, li, B, H, W):
     assert torch.isfinite(two.float()).all() and torch.equal(one, two)
 
 
+@pytest.mark.parametrize("li,B,H,W", [(4, 2, 60, 80), (4, 1, 16, 8), (5, 3, 60, 80), (5, 1, 16, 8), (6, 5, 30, 40),
+                                      (7, 1, 16, 8), (8, 3, 30, 40), (8, 1, 34, 50), (10, 2, 30, 40), (6, 9, 30, 40)])
+def test_cta_pair_kernels_equal_single_cta(net, li, B, H, W):
+    """>= 128-channel layers on CTA pairs (tcgen05.mma.cta_group::2, each CTA holds half of every weight block; odd
+    tile counts end in dummy tiles) == the single-CTA kernels, bit for bit (same per-row accumulation order)."""
+    from pytorch_superpoint_b200 import _lib
+    L = _lib.lib()
+    torch.manual_seed(li + W)
+    x = (torch.randn(B, H, W, SHAPES[li][0], device="cuda") * 0.5).to(torch.bfloat16).contiguous()
+    try:
+        L.spb_conv_tc_set_cg2(0)
+        one = _layer(net, li, x, B, H, W, "tcgen05")
+        L.spb_conv_tc_set_cg2(2)  # every layer that has a pair kernel (incl. 64 -> 128, off by default)
+        two = _layer(net, li, x, B, H, W, "tcgen05")
+    finally:
+        L.spb_conv_tc_set_cg2(1)
+    assert torch.isfinite(two.float()).all() and torch.equal(one, two)
+
+
 @pytest.mark.parametrize("B,H,W", [(1, 16, 8), (3, 24, 40), (2, 240, 320), (5, 30, 52)])
 def test_conv1a_tensor_core_vs_simt(net, B, H, W):
     """conv1a as a K=16 im2col MMA: same bf16 numerics as the CUDA-core kernel, incl. ragged last tile."""
