@@ -418,8 +418,8 @@ int conv_tc2(const LayerDev& L, const __nv_bfloat16* in, void* out, int B, int H
   if (!g_cg2 || out_mode != 0 || L.ks != 3 || !L.relu) return SPB_OK;
   __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out);
   *handled = true;
-  // (64 -> 128, weights resident: a tile is only 2304 MMA cycles, the pair's lock-step round trip shows -- the
-  // single-CTA kernel is 8 % faster there; kept instantiated for the tests behind g_cg2 == 2)
+  // (64 -> 128, weights resident: measured 0.407 ms per 800 views on one CTA, 0.427 on a CTA pair, 0.409 on a CTA
+  // pair with tile pairs -- the layer is not operand-read bound; kept instantiated for the tests behind g_cg2 == 2)
   if (L.cin == 64 && L.cout_pad == 128 && !L.pool && g_cg2 == 2)
     return launch2<Cfg2<64, 128, true, 3, 0, false, 1>>(L, in, o, B, H, W, st);
   if (L.cin == 128 && L.cout_pad == 128)
