@@ -49,30 +49,6 @@ struct S3Args {
   int B, H, W, tiles_x, tiles_y, ntiles;
 };
 
-// 16 fp32 channels of one pixel (bias added) -> bf16x2 -> ReLU -> optional 2x2 max-pool (partners lane^1, lane^16)
-template <bool POOL>
-__device__ __forceinline__ void s3_pack16(const float (&f)[16], uint32_t* pk) {
-  const __nv_bfloat162 zero = __floats2bfloat162_rn(0.f, 0.f);
-#pragma unroll
-  for (int j = 0; j < 16; j += 4) {
-    __nv_bfloat162 h0 = __hmax2(__floats2bfloat162_rn(f[j], f[j + 1]), zero);
-    __nv_bfloat162 h1 = __hmax2(__floats2bfloat162_rn(f[j + 2], f[j + 3]), zero);
-    uint32_t u0 = *reinterpret_cast<const uint32_t*>(&h0), u1 = *reinterpret_cast<const uint32_t*>(&h1);
-    if (POOL) {
-#pragma unroll
-      for (int sh = 1; sh <= 16; sh <<= 4) {
-        const uint32_t p0 = __shfl_xor_sync(0xffffffffu, u0, sh), p1 = __shfl_xor_sync(0xffffffffu, u1, sh);
-        h0 = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&u0), *reinterpret_cast<const __nv_bfloat162*>(&p0));
-        h1 = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&u1), *reinterpret_cast<const __nv_bfloat162*>(&p1));
-        u0 = *reinterpret_cast<const uint32_t*>(&h0);
-        u1 = *reinterpret_cast<const uint32_t*>(&h1);
-      }
-    }
-    pk[j / 2] = u0;
-    pk[j / 2 + 1] = u1;
-  }
-}
-
 #ifndef SPB_S3_TOKEN_R
 #define SPB_S3_TOKEN_R 0  // the issue token is handed over behind this tap row (0, 1 and 2 measure the same)
 #endif

@@ -1064,9 +1064,10 @@ extern "C" int spb_conv1_fused_set_probe(long long* dev_buf) {  // debug: timeli
   g_conv1_dbg = dev_buf;
   return SPB_OK;
 }
-static int g_fuse1 = 1;  // conv1a fused into conv1b's kernel (0: two kernels, for A/B tests)
+static int g_fuse1 = 1;  // conv1a fused into conv1b's kernel: 0 two kernels (A/B tests), 1 shifted-window conv1b
+                         // (conv1_fused_kernel), 2 column-stacked N=192 conv1b (conv1_s3.cu)
 extern "C" int spb_conv_tc_set_fuse1(int on) {
-  g_fuse1 = on ? 1 : 0;
+  g_fuse1 = on < 0 ? 0 : on > 2 ? 2 : on;
   return SPB_OK;
 }
 bool conv1_fused_enabled() { return g_fuse1 != 0; }
@@ -1079,6 +1080,7 @@ int conv1_fused(const LayerDev& L1a, const LayerDev& L1b, const float* x, __nv_b
     set_error("conv1_fused: needs even H and W %% 4 == 0 (got %dx%d)", H, W);
     return SPB_EINVAL;
   }
+  if (g_fuse1 == 2) return conv1_s3(L1a, L1b, x, out, V, H, W, st);
   CUtensorMap tm_w2;
   memcpy(&tm_w2, L1b.tmap_w, sizeof(tm_w2));
   Conv1FusedArgs a;

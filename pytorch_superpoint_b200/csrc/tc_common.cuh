@@ -86,6 +86,12 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
 template <int BW>
 __device__ __forceinline__ void tc_ld_nowait(uint32_t taddr, uint32_t (&v)[BW]);
 template <>
+__device__ __forceinline__ void tc_ld_nowait<8>(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr));
+}
+template <>
 __device__ __forceinline__ void tc_ld_nowait<16>(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -221,5 +227,32 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 EncodeTiledFn get_encode();  // conv_tc.cu
 // bf16 NHWC activations [B,H,W,C] as a 4-D tensor map with a (64 ch, boxw px, boxh rows, 1) SWIZZLE_128B box
 int encode_act_map(CUtensorMap* tm, const void* in, int B, int H, int W, int C, int boxw, int boxh);
+
+// 4 fp32 channels of one pixel (bias added) -> bf16x2 -> ReLU -> optional 2x2 max-pool (partners lane^1, lane^16)
+template <bool POOL>
+__device__ __forceinline__ void s3_pack4(const float* f, uint32_t* pk) {
+  const __nv_bfloat162 zero = __floats2bfloat162_rn(0.f, 0.f);
+  __nv_bfloat162 h0 = __hmax2(__floats2bfloat162_rn(f[0], f[1]), zero);
+  __nv_bfloat162 h1 = __hmax2(__floats2bfloat162_rn(f[2], f[3]), zero);
+  uint32_t u0 = *reinterpret_cast<const uint32_t*>(&h0), u1 = *reinterpret_cast<const uint32_t*>(&h1);
+  if (POOL) {
+#pragma unroll
+    for (int sh = 1; sh <= 16; sh <<= 4) {
+      const uint32_t p0 = __shfl_xor_sync(0xffffffffu, u0, sh), p1 = __shfl_xor_sync(0xffffffffu, u1, sh);
+      h0 = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&u0), *reinterpret_cast<const __nv_bfloat162*>(&p0));
+      h1 = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&u1), *reinterpret_cast<const __nv_bfloat162*>(&p1));
+      u0 = *reinterpret_cast<const uint32_t*>(&h0);
+      u1 = *reinterpret_cast<const uint32_t*>(&h1);
+    }
+  }
+  pk[0] = u0;
+  pk[1] = u1;
+}
+// 16 channels: four groups of 4
+template <bool POOL>
+__device__ __forceinline__ void s3_pack16(const float (&f)[16], uint32_t* pk) {
+#pragma unroll
+  for (int j = 0; j < 16; j += 4) s3_pack4<POOL>(f + j, pk + j / 2);
+}
 
 }  // namespace spb
