@@ -1064,6 +1064,7 @@ extern "C" int spb_conv1_fused_set_probe(long long* dev_buf) {  // debug: timeli
   g_conv1_dbg = dev_buf;
   return SPB_OK;
 }
+long long* conv1_probe_buf() { return g_conv1_dbg; }
 static int g_fuse1 = 1;  // conv1a fused into conv1b's kernel: 0 two kernels (A/B tests), 1 shifted-window conv1b
                          // (conv1_fused_kernel), 2 column-stacked N=192 conv1b (conv1_s3.cu)
 extern "C" int spb_conv_tc_set_fuse1(int on) {
