@@ -156,6 +156,11 @@ int spb_net_set_impl(spb_net* net, int impl); /* SPB_IMPL_* (default TCGEN05) */
 /* views processed per pass by spb_ha_heatmap_sums (0 = all N at once); bounds the workspace and lets
  * the inter-layer activations of a pass stay L2-resident */
 int spb_net_set_ha_chunk(spb_net* net, int views);
+/* spb_ha_heatmap_sums_batch with more than one pass: run the image warp of the next pass and the aggregate of the
+ * previous one on an internal side stream under the detector net of the current pass (results are bit-identical,
+ * the call still completes in the caller's stream).  Default 0 = strictly sequential passes: under the power cap the
+ * overlap measured +1.5 % at best. */
+int spb_net_set_ha_overlap(spb_net* net, int on);
 /* Measurement hooks (bench.py roofline): record CUDA events on the launch stream around every stage
  * (0..11 = layers conv1a..convDb, 12 = image warp, 13 = fused aggregate) while on != 0;
  * spb_net_profile_read synchronises those events, returns summed milliseconds and launch counts per

@@ -46,6 +46,7 @@ PROTOTYPES = {
     "spb_net_destroy": (_i, [_p]),
     "spb_net_set_impl": (_i, [_p, _i]),
     "spb_net_set_ha_chunk": (_i, [_p, _i]),
+    "spb_net_set_ha_overlap": (_i, [_p, _i]),
     "spb_net_profile": (_i, [_p, _i]),
     "spb_net_profile_read": (_i, [_p, _p, _p]),
     "spb_net_workspace_bytes": (_z, [_i, _i, _i, _i]),

@@ -32,6 +32,11 @@ struct Net {
   int profile;   // record CUDA events around every stage launch (bench / roofline only)
   ProfRec* recs;
   int nrecs, caprecs, usedrecs;
+  // spb_ha_heatmap_sums_batch with more than one pass: image warp of pass c+1 and the aggregate of pass c-1 run on
+  // this stream, under the detector net of pass c (created on first use)
+  int ha_overlap;  // 0 (default) / 1
+  cudaStream_t aux;
+  cudaEvent_t ev_begin, ev_warp[2], ev_fwd[2], ev_agg[2];
 };
 
 // conv_simt.cu

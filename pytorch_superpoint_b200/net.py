@@ -212,6 +212,11 @@ class SuperPointNet_b200(nn.Module):
                                                     torch.cuda.current_stream().cuda_stream), "ha_heatmap_sums_ragged")
         return sums
 
+    def set_ha_overlap(self, on: bool, device=None) -> None:
+        """Overlap the image warp / aggregate of neighbouring passes with the detector net (default off)."""
+        dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        _lib.check(_lib.lib().spb_net_set_ha_overlap(self.handle(dev), int(bool(on))), "set_ha_overlap")
+
     def ha_heatmap_sums_batch(self, imgs, mats_unwarp, mats_fwd, sums=None, accumulate=False, chunk: int = 0):
         """imgs [B,H,W] cuda fp32; mats [N,3,3] shared by the batch or [B,N,3,3] -> sums [B,2,H,W].
         All B*N views go through the kernels in passes of at most ``chunk`` views (0 = library default)."""
