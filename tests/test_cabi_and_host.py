@@ -119,5 +119,8 @@ def test_cabi_argument_errors_without_a_gpu():
     assert L.spb_ha_heatmap_sums_ragged(None, p(buf), p(buf), p(buf), p(ibuf), p(ibuf), 1, 1, 1, 8, 8, p(buf), 0, p(buf),
                                         64, None) < 0
     assert L.spb_ha_workspace_bytes_ragged(0, 1, 1, 8, 8) == 0
+    # pass-overlap switch and pass size: a NULL network handle
+    assert L.spb_net_set_ha_overlap(None, 1) < 0
+    assert L.spb_net_set_ha_chunk(None, 100) < 0
     with pytest.raises(RuntimeError, match="libspb200"):
         _lib.check(-1, "demo")
