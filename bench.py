@@ -1,24 +1,34 @@
 #!/usr/bin/env python
 """bench.py -- HA-export throughput (BASELINE.json metric) on N B200s, one process per GPU.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c2|c3|c4|c5|c1]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A "step" is one pass of the hot path over one batch of synthetic input: IMAGES 240x320 images, each
-homography-adapted with 100 homographies (configs[1]: magicpoint_coco_export.yaml shape): image warp x100 ->
-detector network -> fused softmax/d2s/un-warp/aggregate -> (NCCL all-reduce when the homographies are sharded
-over ranks) -> divide -> threshold + greedy NMS + top-600.  Rank 0 prints ONE JSON line.
+Workloads (BASELINE.json configs; the default c2 is the configuration the metric is quoted on):
+  c2  HA export, 100 homographies x 240x320 (configs[1], magicpoint_coco_export.yaml shape), top-600
+  c4  HA export, 100 homographies x 384x1248 (configs[3], magicpoint_kitti_export.yaml shape)
+  c5  HA export, 100 homographies x 480x640 + descriptors at the key-points + two-way matching of image pairs
+      (configs[4]: HPatches shape, homographies sharded over the GPUs with the NCCL exchange of the summed planes)
+  c3  single-frame extraction, batch 64 at 240x320, top-k 1000 (configs[2]);  c1: the same with ONE image (configs[0])
+
+A "step" is one pass of the hot path over one batch of synthetic input: IMAGES x n_gpus images (weak scaling: every
+GPU works on the same number of views per step at every N), each homography-adapted: image warp x100 -> detector
+network -> fused softmax/d2s/un-warp/aggregate -> (NCCL reduce-scatter of the summed planes over the image dimension
+when the homographies are sharded over ranks) -> divide -> threshold + greedy NMS + top-k.  Rank 0 prints ONE JSON line.
 
   value      images/s with inputs resident in HBM (CUDA events, barrier + synchronize both sides, max over ranks)
-  e2e        same metric through HAExporter.export_batch with pinned HOST images in and HOST key-points out
+  e2e        same metric through HAExporter.submit/collect with pinned HOST images in and HOST key-points out
   roofline   the dominant kernel (conv1_fused_kernel: conv1a+conv1b+pool, 44 % of the conv FLOPs) against the
-             measured bf16 tensor peak
-  cpu_baseline  the CPU oracle port of the reference path on this box's host cores (rank 0, N=1 only)
-  --impl reference   times that CPU arm as the main line (bounded sample per step)
+             measured bf16 tensor peak (sustained when the clock record shows the power cap, burst otherwise)
+  cpu_baseline  the reference's own CPU path on this box's host cores (rank 0, N=1 only): the UNMODIFIED reference
+             functions from baseline/_ref when that copy travelled (kind "reference"), else the oracle port
+  shard_check (N>1) a few images recomputed unsharded on rank 0 outside the timed region vs the sharded result
+  --impl reference   times that CPU arm as the main line (one full image, all 100 homographies, per step)
 """
 from __future__ import annotations
 
 import argparse
+import glob
 import json
 import os
 import statistics
@@ -33,18 +43,32 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-H, W, NVIEWS, TOPK, THR, NMS = 240, 320, 100, 600, 0.015, 4
+THR, NMS = 0.015, 4
 METRIC = "ha_export_images_per_s"
 UNIT = "images/s"
-WORKLOAD = ("HA export: 100 homographies x 240x320 (configs[1], magicpoint_coco_export.yaml shape); "
-            "SuperPointNet_gauss2 weights, seeded random init, eval-mode BN folded; thr 0.015, nms 4, top_k 600")
-CONV_GFLOP_DET = 12.161  # conv FLOPs per 240x320 view, detector path only
-# dram__bytes_read.sum + dram__bytes_write.sum of conv1_fused_kernel per view: 0.2461 GB + 1.9083 GB over one 800-view
-# launch (ncu --set full, profiles/r01_ncu_top_kernels.txt); algorithmic = 0.307 MB fp32 in + 2.458 MB pooled bf16 out
-TRAFFIC_BYTES_PER_VIEW = (0.246116e9 + 1.908269e9) / 800
+# conv FLOPs per view, detector path only / with the descriptor head
+WORKLOADS = {
+    "c2": dict(kind="ha", H=240, W=320, N=100, topk=600, images=32, gflop_det=12.161, gflop_full=13.026,
+               name="HA export: 100 homographies x 240x320 (configs[1], magicpoint_coco_export.yaml shape)"),
+    "c4": dict(kind="ha", H=384, W=1248, N=100, topk=600, images=4, gflop_det=75.884, gflop_full=81.282,
+               name="HA export: 100 homographies x 384x1248 (configs[3], magicpoint_kitti_export.yaml shape)"),
+    "c5": dict(kind="ha", H=480, W=640, N=100, topk=1000, images=8, gflop_det=48.643, gflop_full=52.104, match=True,
+               name="HA export: 100 homographies x 480x640 + descriptors + two-way matching of image pairs "
+                    "(configs[4], HPatches shape)"),
+    "c3": dict(kind="extract", H=240, W=320, N=1, topk=1000, images=64, gflop_det=12.161, gflop_full=13.026,
+               name="key-point + descriptor extraction, batch 64 at 240x320, top-k 1000 (configs[2])"),
+    "c1": dict(kind="extract", H=240, W=320, N=1, topk=0, images=1, gflop_det=12.161, gflop_full=13.026,
+               name="single 240x320 image: heat-map, nms_fast (dist 4, conf 0.015), descriptors (configs[0])"),
+}
+NET_NOTE = "SuperPointNet_gauss2 weights, seeded random init, eval-mode BN folded; thr 0.015, nms 4"
 
 
-def structured_images(n, seed=0):
+def workload_name(key):
+    wl = WORKLOADS[key]
+    return f"{key}: {wl['name']}; {NET_NOTE}, top_k {wl['topk']}"
+
+
+def structured_images(n, H, W, seed=0):
     """Seeded synthetic images with edges/corners (random rectangles + noise), fp32 in [0,1]."""
     rng = np.random.RandomState(seed)
     out = np.empty((n, H, W), np.float32)
@@ -62,13 +86,28 @@ def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
             p = json.load(f)
-        return float(p["bf16_tflops_sustained"]), float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json, sustained)"
+        return (float(p["bf16_tflops_sustained"]), float(p["bf16_tflops"]), float(p["hbm_gbs"]),
+                "measured (MEASURED_PEAKS.json)")
     except Exception:
-        return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+        return 1400.0, 1650.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    """DRAM bytes per view of the dominant kernel from the newest ncu --set full summary committed under profiles/
+    (profiles/r*_ncu_traffic.json: {"kernel": ..., "dram_bytes_per_view": ..., "views_per_launch": ..., "source": ...})."""
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_traffic.json")))
+    for f in reversed(files):
+        try:
+            with open(f) as fh:
+                d = json.load(fh)
+            return float(d["dram_bytes_per_view"]), os.path.basename(f)
+        except Exception:
+            continue
+    return None, None
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms while the timed region runs."""
 
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -121,40 +160,111 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port of the reference's path (oracle/ is test infrastructure; here it is the thing TIMED
-# as the CPU baseline, never part of the GPU path)
+# CPU arm.  oracle/ and baseline/_ref are test / baseline infrastructure; here they are the thing TIMED as the CPU
+# baseline, never part of the GPU path.
 # ------------------------------------------------------------------------------------------------------------
-def cpu_step(params, img, mu, mf, views):
-    from oracle import oracle as O
-    return O.ha_export_one(img, mu[:views], mf[:views], params, THR, NMS, TOPK)
+class CpuArm:
+    """One HA-exported image on the host cores: the UNMODIFIED reference functions (baseline/_ref, copied by
+    baseline/install_ref.py in the build container) when present, else the oracle port of the same path."""
+
+    def __init__(self, wl):
+        from oracle import oracle as O
+        self.O, self.wl = O, wl
+        self.cores = os.cpu_count() or 1
+        torch.set_num_threads(self.cores)
+        self.sd = O.synthetic_state_dict("gauss2", seed=1)
+        self.ref = None
+        ref_dir = os.path.join(ROOT, "baseline", "_ref")
+        if os.path.isfile(os.path.join(ref_dir, "export.py")):
+            try:
+                from oracle import refshim
+                refshim.REF = ref_dir
+                self.ref = refshim.load()
+                net = self.ref.nets["gauss2"]()
+                net.load_state_dict(self.sd)
+                net.eval()  # the parity target (DESIGN.md section 1: eval-mode BN); no reference file is edited
+                self.fe = self.ref.frontend(conf_thresh=THR, nms_dist=NMS)
+                self.fe.net = net
+            except Exception as e:  # noqa: BLE001 -- any import problem: fall back to the port, say so
+                self.ref, self.why = None, f"baseline/_ref import failed: {type(e).__name__}: {e}"
+        self.kind = "reference" if self.ref is not None else "port"
+        self.params = None if self.ref is not None else O.canonical_params(self.sd)
+
+    def ha_image(self, img, mu, mf):
+        """img [H,W] numpy, mu / mf [N,3,3] numpy -> float64 [K,3] key-points (export.py:283-328 for one image)."""
+        wl = self.wl
+        if self.ref is None:
+            return self.O.ha_export_one(img, mu, mf, self.params, THR, NMS, wl["topk"])
+        ref, fe = self.ref, self.fe
+        H, W = img.shape
+        x = torch.from_numpy(img)[None, None]
+        inv = torch.from_numpy(mf)
+        with torch.no_grad():
+            warped = ref.inv_warp_image_batch(x.repeat(len(mf), 1, 1, 1), inv, mode="bilinear")     # Coco.py:279
+            mask = ref.compute_valid_mask(torch.tensor([H, W]), inv_homography=inv, erosion_radius=0)[:, None]
+            heat = fe.run(warped, onlyHeatmap=True, train=False)                                      # export.py:309
+            agg = ref.combine_heatmap(heat, torch.from_numpy(mu)[None], mask, device="cpu")           # export.py:310
+        pts = fe.getPtsFromHeatmap(agg.detach().cpu().squeeze().numpy()).transpose()                # export.py:311
+        return pts[:wl["topk"]] if wl["topk"] else pts
+
+    def extract_image(self, img):
+        """Single-frame extraction (export.py:127-145): net -> flatten -> getPtsFromHeatmap -> descriptors."""
+        wl, O = self.wl, self.O
+        x = torch.from_numpy(img)[None, None]
+        if self.ref is None:
+            semi, desc = O.net_forward(self.params, x)
+            pts = O.get_pts_from_heatmap(O.flatten_detection(semi.numpy())[0], THR, NMS)
+            pts = pts[:, :wl["topk"]] if wl["topk"] else pts
+            return pts, O.sample_desc_from_points(desc.numpy(), pts)
+        fe = self.fe
+        with torch.no_grad():
+            out = fe.net(x)
+            heat = self.ref.flattenDetection(out["semi"], tensor=True)
+        pts = fe.getPtsFromHeatmap(heat.squeeze().numpy())
+        pts = pts[:, :wl["topk"]] if wl["topk"] else pts
+        return pts, fe.sample_desc_from_points(out["desc"], pts)
+
+    def sample(self):
+        wl = self.wl
+        if wl["kind"] == "ha":
+            what = (f"one full {wl['H']}x{wl['W']} image with all {wl['N']} homographies per step (warp, mask, net fp32, "
+                    "flatten, combine, NMS, top-k)")
+        else:
+            what = f"one {wl['H']}x{wl['W']} image per step (net fp32, flatten, NMS, descriptor sampling)"
+        src = ("the UNMODIFIED reference functions (baseline/_ref: utils/utils.py, models/model_wrap.py, export.py, "
+               "SuperPointNet_gauss2; net.eval())") if self.ref is not None else "oracle/ (numpy + torch fp32 port)"
+        return f"{what} through {src} on all host threads"
 
 
 def run_reference(args):
-    from oracle import oracle as O
     from pytorch_superpoint_b200.homographies import make_ha_homographies
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    params = O.canonical_params(O.synthetic_state_dict("gauss2", seed=1))
-    imgs = structured_images(2, seed=0)
-    mu, mf = make_ha_homographies(NVIEWS, seed=0)
-    views = args.ref_views
+    wl = WORKLOADS[args.workload]
+    arm = CpuArm(wl)
+    imgs = structured_images(2, wl["H"], wl["W"], seed=0)
+    mu, mf = make_ha_homographies(wl["N"], seed=0)
+
+    def step(i):
+        if wl["kind"] == "ha":
+            arm.ha_image(imgs[i % 2], mu, mf)
+        else:
+            arm.extract_image(imgs[i % 2])
+
     for i in range(args.warmup):
-        cpu_step(params, imgs[i % 2], mu, mf, views)
+        step(i)
     t0 = time.perf_counter()
     for i in range(args.steps):
-        cpu_step(params, imgs[i % 2], mu, mf, views)
-    dt = (time.perf_counter() - t0) / args.steps
-    value = 1.0 / (dt * NVIEWS / views)
-    sample = (f"{views} of the {NVIEWS} homographies of one 240x320 image per step (warp, mask, net fp32, flatten, "
-              f"combine, NMS), time scaled x{NVIEWS / views:g} to a full image")
+        step(i)
+    dt = (time.perf_counter() - t0) / max(args.steps, 1)
+    value = 1.0 / dt
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "views_per_step": views},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args.workload), "images_per_step": 1, "homographies": wl["N"],
+                       "sample": "one image of the workload per step (a bounded sample: the GPU arm's step is a batch)"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.cores, "kind": arm.kind, "sample": arm.sample()},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -163,40 +273,76 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------------------------------------
 def run_b200(args):
+    import ctypes as C
     import torch.distributed as dist
-    from pytorch_superpoint_b200 import SuperPointNet_b200, _lib
-    from pytorch_superpoint_b200.synthetic import synthetic_state_dict
+    from pytorch_superpoint_b200 import SuperPointNet_b200, _lib, ops
     from pytorch_superpoint_b200.export import HAExporter
-    from pytorch_superpoint_b200.homographies import make_ha_homographies
+    from pytorch_superpoint_b200.frontend import SuperPointFrontend_b200
+    from pytorch_superpoint_b200.homographies import sample_ha_homographies_device
+    from pytorch_superpoint_b200.sharding import plan_batch
+    from pytorch_superpoint_b200.synthetic import synthetic_state_dict
 
-    os.environ.pop("NCCL_DEBUG", None)  # keep stdout to the single JSON line (NCCL prints its version banner there)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # (NCCL_DEBUG is left as the caller set it: the communicator lines are the driver's evidence of the rank count;
+        # the JSON line is printed last, after the process group is gone)
         dist.init_process_group("nccl", device_id=dev)
     L = _lib.lib()
+    wl = WORKLOADS[args.workload]
+    H, W, NV, TOPK = wl["H"], wl["W"], wl["N"], wl["topk"]
+    ha = wl["kind"] == "ha"
+    per_gpu = args.images if args.images > 0 else wl["images"]
+    B = per_gpu * world if ha else per_gpu  # weak scaling: the same number of views per GPU and step at every N
 
     net = SuperPointNet_b200()
     net.load_state_dict(synthetic_state_dict("gauss2", seed=1))
     exporter = HAExporter(net, THR, NMS, TOPK, device=dev, chunk=args.chunk)
-    B = args.images
-    imgs_np = structured_images(B, seed=0)
-    # every image gets its OWN 100 homographies, like datasets/Coco.py:262-276.  Resident arm: pre-sampled outside
-    # the timed region.  End-to-end arm: drawn afresh on the GPU inside every step (sampler.cu; all
-    # ranks use the same counter-based seed, so the shards agree on the matrices).
-    from pytorch_superpoint_b200.homographies import sample_ha_homographies_device
+    fe = SuperPointFrontend_b200({"model": {"subpixel": {"enable": False}}}, "", NMS, THR, 0.7, load=False, device=str(dev))
+    fe.net = net
+    imgs_np = structured_images(B, H, W, seed=0)
     imgs_host = torch.from_numpy(imgs_np).pin_memory()  # one collated, pinned [B,H,W] batch (DataLoader style)
     imgs_dev = torch.from_numpy(imgs_np).to(dev)
-    mu_dev, mf_dev = sample_ha_homographies_device(NVIEWS, B, seed=0, device=dev)
-    from pytorch_superpoint_b200 import ops
+    # every image gets its OWN homographies, like datasets/Coco.py:262-276.  Resident arm: pre-sampled outside the
+    # timed region.  End-to-end arm: drawn afresh on the GPU inside every step (sampler.cu; all ranks
+    # use the same counter-based seed, so the shards agree on the matrices).
+    mu_dev = mf_dev = None
+    if ha:
+        mu_dev, mf_dev = sample_ha_homographies_device(NV, B, seed=0, device=dev)
+    own_lo, own_hi = exporter._buffers(B, H, W)["slots"][0]["own"] if ha else (0, B)
+    match_state = {}
+
+    def match_owned(ticket):
+        """c5: descriptors of the owned images at their HA key-points + two-way matching of the pairs (2k, 2k+1), all
+        on the exporter's side stream behind the ticket's NMS (no host synchronisation)."""
+        lo, hi = ticket["own"]
+        if hi - lo < 2:
+            return
+        side = exporter._side
+        x = imgs_dev[lo:hi, None]
+        main = torch.cuda.current_stream()
+        _, desc = net.forward_nhwc(x, want_desc=True)  # main stream: shares the network workspace with the HA passes
+        ready = torch.cuda.Event()
+        ready.record(main)
+        side.wait_event(ready)
+        with torch.cuda.stream(side):
+            d = ops.sample_desc_batch_device(desc, ticket["pts_dev"], ticket["cnt_dev"])  # [nown,cap,256], zero padded
+            res = ops.nn_match_pairs_device(d[0::2], d[1::2], 0.7)
+            match_state["last"] = res
+            ticket["done"] = torch.cuda.Event()
+            ticket["done"].record(side)
+        desc.record_stream(side)
 
     def step_resident():
-        # heat-maps on the current stream; NMS/top-k of this batch on the exporter's side stream (overlaps the
-        # next batch's convolutions).  The closing barrier + device synchronize covers both streams.
-        return exporter.submit_resident(imgs_dev, mu_dev, mf_dev)
+        if ha:
+            t = exporter.submit_resident(imgs_dev, mu_dev, mf_dev)
+            if wl.get("match"):
+                match_owned(t)
+            return t
+        return fe.extract_batch(imgs_dev[:, None], top_k=TOPK)
 
     def barrier():
         if world > 1:
@@ -225,23 +371,31 @@ def run_b200(args):
         clk.window(t_region0, time.monotonic())
     launches = int(L.spb_launch_count() - launches0)
     value = B * args.steps / (ms / 1e3)
+    clocks = clk.summary()
 
     # ---- end to end through the public API: pinned host images in, host key-points out ------------------
-    pending = []
-    e2e_seen = []
+    pending, e2e_seen = [], []
 
     def step_e2e():
-        # pinned host images in -> host key-points out; batch i's NMS + D2H overlap batch i+1, results of batch
-        # i-1 are collected (host numpy arrays) while batch i runs
-        mu_step, mf_step = sample_ha_homographies_device(NVIEWS, B, seed=1 + len(e2e_seen), device=dev)
+        if not ha:  # extraction: H2D of the batch, D2H of key-points + sparse descriptors
+            p_, c_, d_ = fe.extract_batch(imgs_host.to(dev, non_blocking=True)[:, None], top_k=TOPK)
+            return p_.cpu(), c_.cpu(), d_.cpu()
+        # pinned host images in -> host key-points out; batch i's exchange + NMS + D2H overlap batch i+1, results of
+        # batch i-1 are collected (host numpy arrays) while batch i runs
+        mu_step, mf_step = sample_ha_homographies_device(NV, B, seed=1 + len(e2e_seen), device=dev)
         e2e_seen.append(0)
-        pending.append(exporter.submit(imgs_host, mu_step, mf_step))
+        t = exporter.submit(imgs_host, mu_step, mf_step)
+        if wl.get("match"):
+            match_owned(t)
+        pending.append(t)
         if len(pending) > 1:
             exporter.collect(pending.pop(0))
 
     def drain():
         while pending:
             exporter.collect(pending.pop(0))
+        if match_state.get("last") is not None:
+            match_state["last"][3].cpu()  # the match counts of the last batch reach the host before the clock stops
 
     for _ in range(2):
         step_e2e()
@@ -265,67 +419,95 @@ def run_b200(args):
 
     ms_e2e = timed_e2e(args.steps)
     e2e_value = B * args.steps / (ms_e2e / 1e3)
-    h2d = B * H * W * 4  # the homographies are drawn on the device
-    d2h = -(-B // world) * (TOPK * 3 * 4 + 4)
+    h2d = B * H * W * 4  # every rank reads the whole batch (it holds views of every image); homographies: on device
+    cap = TOPK if TOPK else -(-H // 5) * -(-W // 5)
+    d2h = (own_hi - own_lo) * (cap * 3 * 4 + 4) + (0 if ha else B * cap * 256 * 4)
 
     # ---- roofline of the dominant kernel: a profiled pass (CUDA events around every stage launch) -------
     h = net.handle(dev)
-    _lib.check(L.spb_net_profile(h, 1))
+    net.set_profile(True, dev)
     prof_steps = min(args.steps, 10)
     ms_prof = timed(step_resident, prof_steps)
-    import ctypes as C
     st_ms, st_n = (C.c_float * 16)(), (C.c_int * 16)()
     _lib.check(L.spb_net_profile_read(h, st_ms, st_n))
-    _lib.check(L.spb_net_profile(h, 0))
+    net.set_profile(False, dev)
     names = ["conv1a", "conv1b", "conv2a", "conv2b", "conv3a", "conv3b", "conv4a", "conv4b", "convPa", "convPb",
              "convDa", "convDb", "warp", "aggregate"]
     stage_ms = {names[i]: round(st_ms[i] / prof_steps, 4) for i in range(14) if st_n[i]}
-    from pytorch_superpoint_b200.sharding import balanced_view_plan, shard_bounds
-    lo, hi = shard_bounds(NVIEWS, rank, world)
-    views_local = hi - lo  # views per image on this rank ...
-    if world > 1 and NVIEWS % world and B >= world and -(-NVIEWS // world) * B <= 800:
-        views_local = len(balanced_view_plan(B, NVIEWS, rank, world)[0]) / B  # ... averaged over the rotated shares
-    peak_tf, peak_hbm, peak_src = peaks()
+    if ha:
+        ha_views = plan_batch(B, NV, rank, world, net.ha_pass_views(H, W, dev)).local_views
+        views_step = ha_views + ((own_hi - own_lo) if wl.get("match") else 0)
+    else:
+        ha_views, views_step = 0, B
+    peak_sus, peak_burst, peak_hbm, peak_src = peaks()
+    capped = "sw_power_cap" in (clocks.get("reasons") or [])
+    peak_tf = peak_sus if capped else peak_burst  # a kernel timed in an uncapped region is measured against burst
     # stage 1 = conv1_fused_kernel: conv1a (1->64) + conv1b (64->64) + pool in one launch
     k_launches = st_n[1]
     k_ms = st_ms[1] / max(k_launches, 1)
-    views_per_launch = B * views_local * prof_steps / max(k_launches, 1)
+    views_per_launch = views_step * prof_steps / max(k_launches, 1)
     flop_per_launch = 2.0 * H * W * 64 * 9 * (64 + 1) * views_per_launch
     achieved = flop_per_launch / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
     net_ms = sum(st_ms[i] for i in range(12)) / prof_steps
-    # DRAM traffic of that kernel from the ncu --set full capture in profiles/ (bytes per view, measured at
-    # 100 views per launch), scaled to this run's views per launch
-    traffic = TRAFFIC_BYTES_PER_VIEW * views_per_launch if TRAFFIC_BYTES_PER_VIEW else None
+    per_view, traffic_src = ncu_traffic()
+    traffic = per_view * views_per_launch * (H * W) / (240 * 320) if per_view else None
+    det_flop = wl["gflop_det"] * 1e-3 * ha_views + wl["gflop_full"] * 1e-3 * (views_step - ha_views)
     roofline = {"bound": "tensor", "kernel": "conv1_fused_kernel (conv1a+conv1b+pool: 44.2% of the detector's conv FLOPs)",
                 "achieved": round(achieved, 2), "peak": peak_tf, "unit": "TFLOP/s", "frac": round(achieved / peak_tf, 4),
-                "traffic": traffic, "algorithmic_bytes": (H * W * 4 + (H // 2) * (W // 2) * 64 * 2) * views_per_launch,
-                "peak_source": peak_src, "avg_launch_ms": round(k_ms, 4), "launches": int(k_launches),
-                "views_per_launch": views_per_launch,
-                "whole_net_tflops": round(CONV_GFLOP_DET * 1e-3 * B * views_local / (net_ms * 1e-3), 2) if net_ms else None}
+                "frac_of_sustained": round(achieved / peak_sus, 4), "frac_of_burst": round(achieved / peak_burst, 4),
+                "traffic": traffic, "traffic_source": traffic_src,
+                "algorithmic_bytes": (H * W * 4 + (H // 2) * (W // 2) * 64 * 2) * views_per_launch,
+                "peak_source": peak_src + (": sustained (sw_power_cap active in the timed region)" if capped else
+                                           ": burst (no cap in the clock record)"),
+                "avg_launch_ms": round(k_ms, 4), "launches": int(k_launches), "views_per_launch": views_per_launch,
+                "whole_net_tflops": round(det_flop / (net_ms * 1e-3), 2) if net_ms else None,
+                "whole_path_frac": round(value / world * wl["gflop_det"] * 1e-3 * NV / peak_tf, 4) if ha else None}
 
     line = {"metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "images_per_step": B, "homographies": NVIEWS,
-                       "homography_sets": "one set of 100 per image (datasets/Coco.py:262-276); resident arm: pre-sampled; "
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": workload_name(args.workload),
+                       "images_per_step": B, "images_per_gpu_and_step": per_gpu, "homographies": NV,
+                       "homography_sets": "one set per image (datasets/Coco.py:262-276); resident arm: pre-sampled; "
                                           "e2e arm: drawn on the GPU inside every step",
-                       "parallelism": f"homography-sharded x{world} (uneven shares rotated over the images of the batch: "
-                                      f"{B * NVIEWS // world} views per rank and step), 1 NCCL all-reduce of [B,2,H,W] per step",
-                       "l2": "per-image activation working set ~1.3 GB streams through the 126 MB L2 every step "
+                       "parallelism": (f"homography-sharded x{world}: every rank warps / runs the detector on its rotated "
+                                       f"block of the views of EVERY image ({views_step} views per rank and step), ONE NCCL "
+                                       "reduce-scatter of the [B,2,H,W] planes over the image dimension per step, issued "
+                                       "asynchronously; each rank divides / runs NMS on its B/N images") if ha else
+                                      "single GPU batch",
+                       "l2": "per-pass activation working set (~2 GB) streams through the 126 MB L2 every step "
                              "(inputs larger than L2; no explicit flush)", "ha_chunk": args.chunk},
             "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": round(ms_e2e / args.steps, 4)},
             "gpu_launches": launches, "roofline": roofline, "stage_ms_per_step": stage_ms,
-            "profiled_ms_per_step": round(ms_prof / prof_steps, 4), "clocks": clk.summary()}
+            "stage_sum_over_step": round(sum(stage_ms.values()) / (ms_prof / prof_steps), 4),
+            "profiled_ms_per_step": round(ms_prof / prof_steps, 4), "clocks": clocks}
+    if wl.get("match") and match_state.get("last") is not None:
+        line["matches_per_pair"] = round(float(match_state["last"][3].float().mean().item()), 1)
 
-    # ---- second half of the BASELINE metric: single-frame extraction ms/image (configs[2]: batch 64, top-k 1000,
-    # detector + descriptor heads, NMS, sparse descriptors) next to the CPU oracle on one image (configs[0]) -----
-    if rank == 0 and world == 1:
-        from pytorch_superpoint_b200.frontend import SuperPointFrontend_b200
-        fe = SuperPointFrontend_b200({"model": {"subpixel": {"enable": False}}}, "", NMS, THR, 0.7, load=False,
-                                     device=str(dev))
-        fe.net = net
-        xb = torch.from_numpy(structured_images(64, seed=5)[:, None]).to(dev)
+    # ---- N > 1: the sharded result against an unsharded recomputation on rank 0 (outside the timed region) ------
+    if ha and world > 1:
+        t = exporter.submit_resident(imgs_dev, mu_dev, mf_dev)
+        pts_sh = exporter.collect(t)
+        heat_sh = exporter.last_heat(B, H, W).clone()
+        if rank == 0:
+            k = min(own_hi - own_lo, 4)
+            local = HAExporter(net, THR, NMS, TOPK, device=dev, chunk=args.chunk, sharded=False)
+            pts_lo = local.collect(local.submit_resident(imgs_dev[:k].contiguous(), mu_dev[:k].contiguous(),
+                                                         mf_dev[:k].contiguous()))
+            heat_lo = local.last_heat(k, H, W)
+            jac = []
+            for b in range(k):
+                a = {(int(x), int(y)) for x, y, _ in pts_sh[b]}
+                c = {(int(x), int(y)) for x, y, _ in pts_lo[b]}
+                jac.append(len(a & c) / max(len(a | c), 1))
+            line["shard_check"] = {"images": k, "heat_max_abs": float((heat_sh[:k] - heat_lo).abs().max().item()),
+                                   "keypoint_jaccard": round(min(jac), 4),
+                                   "note": "sharded (this run) vs unsharded on rank 0: fp32 summation order only"}
+
+    # ---- second half of the BASELINE metric: single-frame extraction ms/image (configs[2]) next to the CPU arm -----
+    if rank == 0 and world == 1 and ha and args.workload == "c2":
+        xb = torch.from_numpy(structured_images(64, 240, 320, seed=5)[:, None]).to(dev)
         for _ in range(3):
             fe.extract_batch(xb, top_k=1000)
         torch.cuda.synchronize()
@@ -340,38 +522,44 @@ def run_b200(args):
                            "mean_keypoints": round(float(c_.float().mean().item()), 1)}
 
     if rank == 0 and world == 1 and not args.no_cpu:
-        from oracle import oracle as O  # the CPU baseline leg: the one place this arm touches oracle/
-        cores = os.cpu_count() or 1
-        torch.set_num_threads(cores)
-        params = O.canonical_params(synthetic_state_dict("gauss2", seed=1))
-        mu_np, mf_np = mu_dev[0].cpu().numpy(), mf_dev[0].cpu().numpy()  # image 0's matrices, same on both sides
-        cpu_step(params, imgs_np[0], mu_np, mf_np, 5)  # warm-up
-        t0 = time.perf_counter()
-        pts_cpu = cpu_step(params, imgs_np[0], mu_np, mf_np, NVIEWS)
-        dt = time.perf_counter() - t0
-        line["cpu_baseline"] = {"value": round(1.0 / dt, 4), "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": "one full 240x320 image with all 100 homographies through oracle/ "
-                                          "(numpy warp/mask/combine/NMS + torch fp32 conv on all host threads)"}
-        # the same image through the GPU path: key-point overlap with the fp32 CPU oracle (informational)
-        pts_gpu = exporter.export_image(imgs_host[0], mu_dev[0], mf_dev[0])
-        a = {(int(x), int(y)) for x, y, _ in pts_gpu}
-        b = {(int(x), int(y)) for x, y, _ in pts_cpu}
-        line["keypoint_jaccard_vs_cpu_fp32"] = round(len(a & b) / max(len(a | b), 1), 4)
-        # configs[0]: the same single-frame extraction on the host cores (CPU oracle, one image)
-        x1 = torch.from_numpy(structured_images(1, seed=5)[:, None])
-        t0 = time.perf_counter()
-        semi_c, desc_c = O.net_forward(params, x1)
-        pts_c = O.get_pts_from_heatmap(O.flatten_detection(semi_c.numpy())[0], THR, NMS)[:, :1000]
-        O.sample_desc_from_points(desc_c.numpy(), pts_c)
-        line["extract"]["cpu_ms_per_image"] = round((time.perf_counter() - t0) * 1e3, 2)
-    if rank == 0:
-        print(json.dumps(line), flush=True)
+        arm = CpuArm(wl)  # the CPU baseline leg: the one place this arm touches oracle/ and baseline/_ref
+        if ha:
+            mu_np, mf_np = mu_dev[0].cpu().numpy(), mf_dev[0].cpu().numpy()  # image 0's matrices, same on both sides
+            small = min(NV, 5)
+            arm.ha_image(imgs_np[0], mu_np[:small], mf_np[:small])  # warm-up
+            t0 = time.perf_counter()
+            pts_cpu = arm.ha_image(imgs_np[0], mu_np, mf_np)
+            dt = time.perf_counter() - t0
+            # the same image through the GPU path: key-point overlap with the fp32 CPU path (informational)
+            pts_gpu = exporter.export_image(imgs_host[0], mu_dev[0], mf_dev[0])
+            a = {(int(x), int(y)) for x, y, _ in pts_gpu}
+            b = {(int(x), int(y)) for x, y, _ in pts_cpu}
+            line["keypoint_jaccard_vs_cpu_fp32"] = round(len(a & b) / max(len(a | b), 1), 4)
+        else:
+            arm.extract_image(imgs_np[0])
+            t0 = time.perf_counter()
+            for i in range(5):
+                arm.extract_image(imgs_np[i % B])
+            dt = (time.perf_counter() - t0) / 5
+        line["cpu_baseline"] = {"value": round(1.0 / dt, 4), "unit": UNIT, "cores": arm.cores, "kind": arm.kind,
+                                "sample": arm.sample().replace("per step", "(timed once)")}
+        if "extract" in line:  # configs[0]: the same single-frame extraction on the host cores, one image
+            x1 = structured_images(1, 240, 320, seed=5)[0]
+            arm1 = CpuArm(WORKLOADS["c3"])
+            arm1.extract_image(x1)
+            t0 = time.perf_counter()
+            arm1.extract_image(x1)
+            line["extract"]["cpu_ms_per_image"] = round((time.perf_counter() - t0) * 1e3, 2)
+            line["extract"]["cpu_kind"] = arm1.kind
     if world > 1:
         try:
             dist.barrier()
             dist.destroy_process_group()
         except Exception:
             pass
+    if rank == 0:
+        sys.stderr.flush()
+        print("\n" + json.dumps(line), flush=True)  # own line, after NCCL's teardown messages
     return 0
 
 
@@ -381,9 +569,9 @@ def main():
     ap.add_argument("--steps", type=int, default=12)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--images", type=int, default=32, help="images per step (one batch)")
-    ap.add_argument("--chunk", type=int, default=0, help="views per network pass (0 = all of the rank's views)")
-    ap.add_argument("--ref-views", type=int, default=20, help="--impl reference: homographies per step (bounded sample)")
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--images", type=int, default=0, help="images per GPU and step (0 = the workload's default)")
+    ap.add_argument("--chunk", type=int, default=0, help="views per network pass (0 = library default: bounded by bytes)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -106,6 +106,11 @@ int spb_sample_desc_from_points(const float* coarse, int nhwc, const float* pts,
 int spb_sample_desc_from_points_ex(const float* coarse, int nhwc, const float* pts, int pts_stride, const int* count,
                                    int K, int Hc, int Wc, int D, int cell, int normalize, float* out, void* stream);
 
+/* One launch for a batch (the per-image loop of export.py:127-145; Val_model_heatmap.py:151-155 itself is only valid
+ * for B = 1): coarse NHWC [B,Hc,Wc,D], pts [B,K,3], counts [B] (device) -> out [B,K,D], rows behind counts[b] zero. */
+int spb_sample_desc_batch(const float* coarse_nhwc, const float* pts, const int* counts, int B, int K, int Hc, int Wc,
+                          int D, int cell, int normalize, float* out, void* stream);
+
 /* NEXT row f-3 -- models/model_utils.py:24-60 `SuperPointNet_process.pred_soft_argmax`: 5x5 roi_pool patches of the
  * 7x7 window around every labelled pixel (utils/losses.py:16-29,87-98 + torchvision roi_pool bin rule), log, spatial
  * soft-argmax in pixel coordinates (torchgeometry restated: parity unpinned).  heat [B,1,H,W] fp32, idx [N,4] int64
@@ -124,6 +129,9 @@ int spb_dense_desc(const float* coarse_nhwc, int B, int Hc, int Wc, int D, int c
  * restated from its published definition (package not vendored by the reference): parity unpinned. */
 int spb_soft_argmax_points(const float* heat, int H, int W, const float* pts, const int* count, int K,
                            int patch_size, float* dxdy, void* stream);
+/* a batch in one launch: heat [B,H,W], pts [B,K,3], counts [B] (device), dxdy [B,K,2] */
+int spb_soft_argmax_points_batch(const float* heat, int B, int H, int W, const float* pts, const int* counts, int K,
+                                 int patch_size, float* dxdy, void* stream);
 
 /* NEXT row f-1 -- models/model_wrap.py:437-480 `PointTracker.nn_match_two_way`: desc1 [D,K1], desc2 [D,K2] fp32
  * (unit-norm columns, row-major like the reference's M x N arrays).  L2 distance sqrt(2 - 2*clip(d1.d2)), row and
@@ -133,6 +141,14 @@ int spb_soft_argmax_points(const float* heat, int H, int W, const float* pts, co
 size_t spb_nn_match_workspace_bytes(int K1, int K2);
 int spb_nn_match_two_way(const float* desc1, int K1, const float* desc2, int K2, int D, float nn_thresh, int* idx1,
                          int* idx2, float* score, int* count, void* ws, size_t ws_bytes, void* stream);
+
+/* The same for P image pairs in one launch and without a host round trip (export.py:147-151 per pair): desc1 / desc2
+ * [P,K,D] in the descriptor sampler's point-major layout, rows behind an image's key-point count zero filled (a zero
+ * row is sqrt(2) away from every unit descriptor: it can neither pass nn_thresh < sqrt(2) nor beat a real match).
+ * idx1 / idx2 / score [P,K], count [P] (all device). */
+size_t spb_nn_match_pairs_workspace_bytes(int P, int K);
+int spb_nn_match_pairs(const float* desc1, const float* desc2, int P, int K, int D, float nn_thresh, int* idx1,
+                       int* idx2, float* score, int* count, void* ws, size_t ws_bytes, void* stream);
 
 /* NEXT row f-2 -- utils/homographies.py:12-141 `sample_homography_np` as called by datasets/Coco.py:262-276:
  * `total` homographies (image b owns [b*per_image, (b+1)*per_image); index 0 of every image is the identity when
@@ -153,8 +169,8 @@ typedef struct spb_net spb_net;
 int spb_net_create(spb_net** net, const float* const* weights, const float* const* biases);
 int spb_net_destroy(spb_net* net);
 int spb_net_set_impl(spb_net* net, int impl); /* SPB_IMPL_* (default TCGEN05) */
-/* views processed per pass by spb_ha_heatmap_sums (0 = all N at once); bounds the workspace and lets
- * the inter-layer activations of a pass stay L2-resident */
+/* views processed per pass by spb_ha_heatmap_sums* (0 = the default: bounded by bytes, 800 x 240 x 320 pixels of
+ * views per pass); bounds the workspace */
 int spb_net_set_ha_chunk(spb_net* net, int views);
 /* spb_ha_heatmap_sums_batch with more than one pass: run the image warp of the next pass and the aggregate of the
  * previous one on an internal side stream under the detector net of the current pass (results are bit-identical,
@@ -187,21 +203,35 @@ int spb_ha_heatmap_sums(spb_net* net, const float* img, const float* mats_unwarp
 /* Same for a batch of B images in one set of launches (export.py's per-image loop, batched so that a shard of
  * 12-13 views per image still fills the GPU): imgs [B,H,W]; matrices [N,3,3] shared by all images
  * (shared_mats != 0) or [B,N,3,3]; sums [B,2,H,W].  Views are processed in passes of at most
- * spb_net_set_ha_chunk views (default 800). */
+ * spb_ha_pass_views(net, H, W) views. */
 size_t spb_ha_workspace_bytes_batch(spb_net* net, int B, int N, int H, int W);
 int spb_ha_heatmap_sums_batch(spb_net* net, const float* imgs, const float* mats_unwarp, const float* mats_fwd,
                               int shared_mats, int B, int N, int H, int W, float* sums, int accumulate, void* ws,
                               size_t ws_bytes, void* stream);
 
-/* Balanced homography sharding (a rank's share of 100 views over 8 ranks is 12 or 13 per image; rotating the
- * larger shares over the images of a batch gives every rank the same number of views per step): V views as a flat
- * list, view v belongs to image view_image[v] (device int[V], grouped by image in ascending order) and image b owns
- * the views [view_offsets[b], view_offsets[b+1]) (device int[B+1]); mats_* [V,3,3] in view order.  One pass, so V is
- * bounded by the workspace the caller provides. */
+/* The image side of the HA branch on its own -- datasets/Coco.py:279-282 (`inv_warp_image_batch` of the repeated image
+ * + `compute_valid_mask`) with the kernels of the fused pass: imgs [nb,H,W]; view v is image view_image[v] (device
+ * int[V]) warped by mats_fwd[view_mat[v]] (view_mat NULL: mats_fwd[v]).  views [V,H,W] fp32 (folded coordinates:
+ * within ~1e-3 of spb_inv_warp_image_batch), bits [V,H,W/8]: bit (x % 8) of byte x / 8 = the valid mask of pixel x,
+ * EXACTLY spb_compute_valid_mask.  W % 8 == 0. */
+size_t spb_ha_warp_views_workspace_bytes(int nb, int V, int H, int W);
+int spb_ha_warp_views(const float* imgs, const float* mats_fwd, const int* view_image, const int* view_mat, int nb,
+                      int V, int H, int W, float* views, uint8_t* bits, void* ws, size_t ws_bytes, void* stream);
+
+/* Homography sharding (pytorch_superpoint_b200/sharding.py; replaces nn.DataParallel, export.py:265): a rank's share
+ * of 100 views over 8 ranks is 12 or 13 per image and the larger shares rotate over the images of a batch, so a pass
+ * is a flat list of V views: view v belongs to image view_image[v] (device int[V], grouped by image in ascending
+ * order, relative to imgs), uses the matrices mats_*[view_mat[v]] (device int[V]; NULL: the matrices are listed in
+ * view order) and image b owns the views [view_offsets[b], view_offsets[b+1]) (device int[B+1]); sums [B,2,H,W].
+ * ONE pass: V is bounded by the workspace the caller provides; spb_ha_pass_views(net, H, W) is the number of views
+ * the library itself puts into a pass (bounded by bytes: 800 at 240x320, 200 at 480x640, 128 at 384x1248; or the
+ * spb_net_set_ha_chunk value). */
+int spb_ha_pass_views(spb_net* net, int H, int W);
 size_t spb_ha_workspace_bytes_ragged(int B, int V, int max_views_per_image, int H, int W);
 int spb_ha_heatmap_sums_ragged(spb_net* net, const float* imgs, const float* mats_unwarp, const float* mats_fwd,
-                               const int* view_image, const int* view_offsets, int B, int V, int max_views_per_image,
-                               int H, int W, float* sums, int accumulate, void* ws, size_t ws_bytes, void* stream);
+                               const int* view_image, const int* view_mat, const int* view_offsets, int B, int V,
+                               int max_views_per_image, int H, int W, float* sums, int accumulate, void* ws,
+                               size_t ws_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -38,6 +38,10 @@ PROTOTYPES = {
     "spb_roi_soft_argmax": (_i, [_p, _i, _i, _i, _p, _i, _p, _p, _p]),
     "spb_dense_desc": (_i, [_p, _i, _i, _i, _i, _i, _p, _p]),
     "spb_soft_argmax_points": (_i, [_p, _i, _i, _p, _p, _i, _i, _p, _p]),
+    "spb_soft_argmax_points_batch": (_i, [_p, _i, _i, _i, _p, _p, _i, _i, _p, _p]),
+    "spb_sample_desc_batch": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
+    "spb_nn_match_pairs_workspace_bytes": (_z, [_i, _i]),
+    "spb_nn_match_pairs": (_i, [_p, _p, _i, _i, _i, _f, _p, _p, _p, _p, _p, _z, _p]),
     "spb_nn_match_workspace_bytes": (_z, [_i, _i]),
     "spb_nn_match_two_way": (_i, [_p, _i, _p, _i, _i, _f, _p, _p, _p, _p, _p, _z, _p]),
     "spb_sample_ha_homographies": (_i, [C.c_ulonglong, _i, _i, _i, _i, _i, _i, _i, _i, C.c_double, C.c_double, C.c_double,
@@ -56,7 +60,10 @@ PROTOTYPES = {
     "spb_ha_heatmap_sums": (_i, [_p, _p, _p, _p, _i, _i, _i, _p, _i, _p, _z, _p]),
     "spb_ha_workspace_bytes_batch": (_z, [_p, _i, _i, _i, _i]),
     "spb_ha_workspace_bytes_ragged": (_z, [_i, _i, _i, _i, _i]),
-    "spb_ha_heatmap_sums_ragged": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _i, _p, _z, _p]),
+    "spb_ha_pass_views": (_i, [_p, _i, _i]),
+    "spb_ha_warp_views_workspace_bytes": (_z, [_i, _i, _i, _i]),
+    "spb_ha_warp_views": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _z, _p]),
+    "spb_ha_heatmap_sums_ragged": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _i, _p, _z, _p]),
     "spb_ha_heatmap_sums_batch": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _i, _p, _z, _p]),
 }
 # debug knobs exported by the library but not part of the public header

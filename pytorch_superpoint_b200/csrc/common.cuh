@@ -137,6 +137,110 @@ __device__ __forceinline__ float bilinear_fast(const Taps& t, int W, int H, F&& 
   return acc;
 }
 
+// View v of a pass -> its source image (relative to the pass's first image) and its matrix (index into the matrix
+// arrays the caller passed): explicit per-view index arrays (homography sharding: rotated view blocks, a different
+// number of views per image) or arithmetic (vpi views per image; matrices shared by the images or image-major).
+struct ViewMap {
+  const int* view_image;  // device int[V] or NULL
+  const int* view_mat;    // device int[V] or NULL
+  int vpi, shared;
+  __device__ __forceinline__ int img(int v) const { return view_image ? __ldg(view_image + v) : v / vpi; }
+  __device__ __forceinline__ int mat(int v) const {
+    return view_mat ? __ldg(view_mat + v) : (shared ? v % vpi : v);
+  }
+};
+
+// ---- fast coordinate pipeline of the fused HA path (ha_fast.cu) -----------------------------------------------
+// The generic operators above evaluate the reference's coordinate expression with one rounding per operation (bit
+// exact against the oracle).  Inside the fused HA path the warped views feed a bf16 network and the un-warped
+// probabilities a 1e-2 heat-map tolerance, so there the homography is folded ONCE per view (in double) into
+//   s = (a0*x + a1*y + a2) / (c0*x + c1*y + c2)        x, y = integer output pixel
+// which yields the sample position in a zero-PADDED source frame, already offset by +0.5 for the rounding trick
+// (kHaPad border pixels on every side: no per-tap validity tests, coordinates are clamped into the border).
+// Only the valid-mask bit stays exact: it is decided from s when s is further than an epsilon from a decision
+// boundary and re-evaluated with the exact pipeline otherwise.
+constexpr int kHaPad = 2;          // zero border of the padded fp32 source images (pixels, every side)
+constexpr int kHeatPadX = 8;       // left/right border of the fp16 probability planes (16-byte aligned rows)
+constexpr int kHeatPadY = 2;       // top/bottom border rows of the fp16 probability planes
+constexpr unsigned short kHeatMasked = 0xBC00u;  // fp16 -1: "this warped pixel is outside the source image"
+
+struct __align__(16) FoldMat {
+  float ax0, ax1, ax2, ay0;
+  float ay1, ay2, z0, z1;
+  float z2, r0, r1, r2;
+};
+
+// padx / pady: position of pixel (0, 0) inside the padded frame
+__device__ __forceinline__ FoldMat fold_homography(const float* __restrict__ m, int W, int H, int padx, int pady) {
+  const double sx = W > 1 ? 2.0 / (double)(W - 1) : 0.0, sy = H > 1 ? 2.0 / (double)(H - 1) : 0.0;
+  double M[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) M[i] = (double)m[i];
+  // u = sx*x - 1, v = sy*y - 1  ->  row_i . (u, v, 1) = (M[i0]*sx) x + (M[i1]*sy) y + (M[i2] - M[i0] - M[i1])
+  double P[9];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    P[3 * r] = M[3 * r] * sx;
+    P[3 * r + 1] = M[3 * r + 1] * sy;
+    P[3 * r + 2] = M[3 * r + 2] - M[3 * r] - M[3 * r + 1];
+  }
+  const double cx = 0.5 * (double)(W - 1), cy = 0.5 * (double)(H - 1);
+  const double ox = (double)padx + 0.5, oy = (double)pady + 0.5;
+  FoldMat f;
+  f.ax0 = (float)(cx * (P[0] + P[6]) + ox * P[6]);
+  f.ax1 = (float)(cx * (P[1] + P[7]) + ox * P[7]);
+  f.ax2 = (float)(cx * (P[2] + P[8]) + ox * P[8]);
+  f.ay0 = (float)(cy * (P[3] + P[6]) + oy * P[6]);
+  f.ay1 = (float)(cy * (P[4] + P[7]) + oy * P[7]);
+  f.ay2 = (float)(cy * (P[5] + P[8]) + oy * P[8]);
+  f.z0 = (float)P[6];
+  f.z1 = (float)P[7];
+  f.z2 = (float)P[8];
+  // r0: half-width (pixels) of the band around a valid-mask decision boundary inside which the bit is re-evaluated
+  // exactly.  The folded and the reference expression differ by a few 1e-4 pixels while the denominator is O(1);
+  // cancellation in the denominator amplifies that by (sum of its term magnitudes) / |Z|, so the band grows with
+  // it, and a view whose denominator changes sign inside the frame is evaluated exactly everywhere.
+  const double zc[4] = {P[8], P[6] * (W - 1) + P[8], P[7] * (H - 1) + P[8], P[6] * (W - 1) + P[7] * (H - 1) + P[8]};
+  double zmin = fabs(zc[0]);
+  bool flip = false;
+#pragma unroll
+  for (int i = 1; i < 4; ++i) {
+    zmin = fmin(zmin, fabs(zc[i]));
+    flip = flip || (zc[i] > 0.0) != (zc[0] > 0.0);
+  }
+  const double zmag = fabs(P[6]) * (W - 1) + fabs(P[7]) * (H - 1) + fabs(P[8]);
+  const double base = 2e-3 + 8e-6 * (double)(W > H ? W : H);
+  const double amp = (zmin > 0.0 && !flip) ? fmax(1.0, zmag / zmin) : 1e30;
+  f.r0 = (float)fmin(base * amp, 1e30);
+  if (!(f.r0 == f.r0)) f.r0 = 1e30f;  // NaN matrix
+  f.r1 = f.r2 = 0.f;
+  return f;
+}
+
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// s in [lo, hi] (already offset by +0.5) -> n = floor(s - 0.5) + 1 as the low bits of a float in [2^23, 2^24) and the
+// two linear weights of the taps n - 1 and n.  Ties (s - 0.5 an exact integer) may round either way; both choices
+// give the same interpolated value.
+struct Tap1 {
+  unsigned bits;  // 0x4B000000 + n
+  float w0, w1;
+};
+__device__ __forceinline__ Tap1 tap_axis(float s, float lo, float hi) {
+  const float c = fminf(fmaxf(s, lo), hi);  // NaN -> lo
+  const float t = __fadd_rn(c, 8388608.f);
+  const float d = __fsub_rn(c, __fsub_rn(t, 8388608.f));
+  Tap1 r;
+  r.bits = __float_as_uint(t);
+  r.w1 = d + 0.5f;
+  r.w0 = 0.5f - d;
+  return r;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

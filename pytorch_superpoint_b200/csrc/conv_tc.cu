@@ -23,7 +23,9 @@ namespace spb {
 // configuration
 // ------------------------------------------------------------------------------------------------
 // OUT_: 0 = ReLU + bf16 NHWC (encoder / head 3x3), 1 = raw fp32 rows staged through shared memory for coalesced
-// stores (convPb: 65 channels), 2 = fp32 rows L2-normalised over the channels (convDb).
+// stores (convPb: 65 channels), 2 = fp32 rows L2-normalised over the channels (convDb), 3 = softmax probabilities
+// [.,64] fp32 (convPb, dustbin dropped), 4 = the same probabilities written as fp16 planes with the depth-to-space
+// indexing and the valid mask applied (convPb inside the HA pass; consumed by ha_fast.cu).
 // NT_: output tiles per accumulator stage.  With streamed weights (128 -> 128) every weight block that arrives in shared
 // memory is used for TWO tiles (8 MMAs instead of 4): the layer was bound by L2 -> SM weight traffic (288 KB per tile).
 template <int CIN_, int NPAD_, int KS_, bool HALO_, bool BRES_, int NA_, int NB_, bool POOL_, int OUT_, int NT_ = 1>
@@ -65,6 +67,7 @@ struct ConvCfg {
 struct ConvArgs {
   const float* bias;
   void* out;
+  const void* aux;  // OUT == 4: valid-mask bits [B, 8H, W] of the warped views
   int B, H, W, cout;
   int tiles_x, tiles_y, ntiles;  // ntiles = real tiles; super-tile s covers tiles s*NT .. s*NT+NT-1 (missing ones are
   int nst;                       // dummies in image B: TMA zero-fills their loads and clips their stores)
@@ -311,7 +314,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) conv_tc_kernel(const __grid_con
         }
         norm = sqrtf(ss);
       }
-      if (C::OUT == 3) {
+      if (C::OUT == 3 || C::OUT == 4) {
         // convPb in the HA path: 65-way softmax of the cell in registers (each thread holds its whole row),
         // dustbin dropped, probabilities written as [.,64] fp32 -- utils/utils.py:514-523 fused here.
         uint32_t w[80];
@@ -339,6 +342,31 @@ __global__ void __launch_bounds__(C::THREADS, 1) conv_tc_kernel(const __grid_con
           sum += e;
         }
         const float rs = __frcp_rn(sum);
+        if constexpr (C::OUT == 4) {
+          // depth-to-space + mask + fp16 in the store (utils/d2s.py:8-25, export.py:52): row r of the 8x8 cell is
+          // 16 bytes of plane row 8y + r; the 8 lanes of a cell row of the tile write 128 contiguous bytes.
+          // A pixel of the warped view that lies outside the source image (mask bit 0) is stored as kHeatMasked.
+          if (valid && t < a.ntiles) {
+            const int Wh = a.W * 8 + 2 * kHeatPadX, Hh = a.H * 8 + 2 * kHeatPadY;
+            const uint8_t* mb = static_cast<const uint8_t*>(a.aux) + ((long long)n * (a.H * 8) + y * 8) * a.W + x;
+            __half* o = static_cast<__half*>(a.out) + ((long long)n * Hh + y * 8 + kHeatPadY) * Wh + kHeatPadX + x * 8;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+              const unsigned m = __ldg(mb + r * a.W);
+              uint32_t pk[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const __half2 h = __floats2half2_rn(__uint_as_float(w[r * 8 + 2 * q]) * rs,
+                                                    __uint_as_float(w[r * 8 + 2 * q + 1]) * rs);
+                const unsigned b2 = (m >> (2 * q)) & 3u;
+                const unsigned sel = (b2 & 1u) * 0xFFFFu | (b2 >> 1) * 0xFFFF0000u;
+                pk[q] = (*reinterpret_cast<const uint32_t*>(&h) & sel) | ((kHeatMasked * 0x10001u) & ~sel);
+              }
+              *reinterpret_cast<uint4*>(o + (long long)r * Wh) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+          }
+          continue;
+        }
         // stage [pixel][32 floats] x 2 halves (SWIZZLE_128B) and let TMA write the warp's 4 rows x 8 pixels
         uint8_t* stg = sOut + (warp - 2) * 8192;
         if (lane == 0) tma_store_wait_read<0>();  // the previous tile's stores have finished reading the tile
@@ -1149,7 +1177,7 @@ extern "C" int spb_conv_tc_set_halo(int on) {
 
 template <class C>
 static int launch(const LayerDev& L, const __nv_bfloat16* in, void* out, int B, int H, int W, int out_mode,
-                  cudaStream_t st) {
+                  cudaStream_t st, const void* aux) {
   CUtensorMap tm_act, tm_wgt, tm_out;
   memcpy(&tm_wgt, L.tmap_w, sizeof(tm_wgt));
   int rc = encode_act_map(&tm_act, in, B, H, W, L.cin, C::P, C::R);
@@ -1177,12 +1205,13 @@ static int launch(const LayerDev& L, const __nv_bfloat16* in, void* out, int B, 
   ConvArgs a;
   a.bias = L.bias;
   a.out = out;
+  a.aux = aux;
   a.B = B;
   a.H = H;
   a.W = W;
   a.cout = L.cout;
   if (L.pool != (C::POOL ? 1 : 0) || L.relu != (C::OUT == 0 ? 1 : 0) || out_mode != C::OUT ||
-      ((C::OUT == 1 || C::OUT == 3) && L.cout != 65)) {
+      ((C::OUT == 1 || C::OUT == 3 || C::OUT == 4) && L.cout != 65) || (C::OUT == 4 && !aux)) {
     set_error("conv_tc: kernel configuration does not match the layer (pool %d relu %d out_mode %d)", L.pool, L.relu,
               out_mode);
     return SPB_EINVAL;
@@ -1199,7 +1228,7 @@ static int launch(const LayerDev& L, const __nv_bfloat16* in, void* out, int B, 
 }
 
 int conv_tc(const LayerDev& L, const __nv_bfloat16* in, void* out, int B, int H, int W, int out_mode,
-            cudaStream_t st) {
+            cudaStream_t st, const void* aux) {
   if (!L.tmap_w) {
     set_error("conv_tc: layer has no weight tensor map");
     return SPB_EINVAL;
@@ -1217,9 +1246,9 @@ int conv_tc(const LayerDev& L, const __nv_bfloat16* in, void* out, int B, int H,
   }
   const bool halo = g_halo_mode != 0;
 #define SPB_CONV(CIN, NPAD, KS, HALO, BRES, NA, NB, POOL, OUT) \
-  launch<ConvCfg<CIN, NPAD, KS, HALO, BRES, NA, NB, POOL, OUT>>(L, in, out, B, H, W, out_mode, st)
+  launch<ConvCfg<CIN, NPAD, KS, HALO, BRES, NA, NB, POOL, OUT>>(L, in, out, B, H, W, out_mode, st, aux)
 #define SPB_CONV2(CIN, NPAD, KS, HALO, BRES, NA, NB, POOL, OUT) \
-  launch<ConvCfg<CIN, NPAD, KS, HALO, BRES, NA, NB, POOL, OUT, 2>>(L, in, out, B, H, W, out_mode, st)
+  launch<ConvCfg<CIN, NPAD, KS, HALO, BRES, NA, NB, POOL, OUT, 2>>(L, in, out, B, H, W, out_mode, st, aux)
   if (L.ks == 3 && L.cin == 64 && L.cout_pad == 64) {
     if (L.pool) return halo ? SPB_CONV(64, 64, 3, true, true, 4, 0, true, 0) : SPB_CONV(64, 64, 3, false, true, 6, 0, true, 0);
     return halo ? SPB_CONV(64, 64, 3, true, true, 4, 0, false, 0) : SPB_CONV(64, 64, 3, false, true, 6, 0, false, 0);
@@ -1236,6 +1265,7 @@ int conv_tc(const LayerDev& L, const __nv_bfloat16* in, void* out, int B, int H,
     return halo ? SPB_CONV(128, 256, 3, true, false, 2, 4, false, 0) : SPB_CONV(128, 256, 3, false, false, 3, 4, false, 0);
   if (L.ks == 1 && L.cin == 256 && L.cout_pad == 80 && out_mode == 1) return SPB_CONV(256, 80, 1, false, true, 6, 0, false, 1);
   if (L.ks == 1 && L.cin == 256 && L.cout_pad == 80 && out_mode == 3) return SPB_CONV(256, 80, 1, false, true, 6, 0, false, 3);
+  if (L.ks == 1 && L.cin == 256 && L.cout_pad == 80 && out_mode == 4) return SPB_CONV(256, 80, 1, false, true, 6, 0, false, 4);
   if (L.ks == 1 && L.cin == 256 && L.cout_pad == 256 && out_mode == 2) return SPB_CONV(256, 256, 1, false, true, 4, 0, false, 2);
 #undef SPB_CONV
 #undef SPB_CONV2

@@ -16,11 +16,20 @@ __global__ void __launch_bounds__(256) sample_desc_kernel(const float* __restric
                                                           const float* __restrict__ pts,
                                                           const int* __restrict__ count, int K, int Hc, int Wc,
                                                           int D, int cell, float* __restrict__ out, int stride,
-                                                          int normalize) {
+                                                          int normalize, int zero_pad) {
   const int lane = threadIdx.x & 31;
   const int k = blockIdx.x * 8 + (threadIdx.x >> 5);
+  // blockIdx.y = image of a batch: coarse [B,Hc,Wc,D] / [B,D,Hc,Wc], pts [B,K,stride], count [B], out [B,K,D]
+  coarse += (long long)blockIdx.y * Hc * Wc * D;
+  pts += (long long)blockIdx.y * K * stride;
+  out += (long long)blockIdx.y * K * D;
+  if (count) count += blockIdx.y;
   const int n = count ? min(*count, K) : K;
-  if (k >= n) return;
+  if (k >= n) {
+    if (zero_pad && k < K)  // rows behind the image's key-point count: zero descriptors (never matched)
+      for (int c = lane; c < D; c += 32) out[(long long)k * D + c] = 0.f;
+    return;
+  }
   const double x = (double)pts[stride * k], y = (double)pts[stride * k + 1];
   const double halfw = (double)((float)(Wc * cell)) / 2.0, halfh = (double)((float)(Hc * cell)) / 2.0;
   const float gx = (float)(x / halfw - 1.0), gy = (float)(y / halfh - 1.0);
@@ -56,10 +65,25 @@ extern "C" int spb_sample_desc_from_points_ex(const float* coarse, int nhwc, con
   const int blocks = ceil_div(K, 8);
   if (nhwc)
     sample_desc_kernel<true><<<blocks, 256, 0, as_stream(stream)>>>(coarse, pts, count, K, Hc, Wc, D, cell, out,
-                                                                    pts_stride, normalize);
+                                                                    pts_stride, normalize, 0);
   else
     sample_desc_kernel<false><<<blocks, 256, 0, as_stream(stream)>>>(coarse, pts, count, K, Hc, Wc, D, cell, out,
-                                                                     pts_stride, normalize);
+                                                                     pts_stride, normalize, 0);
+  SPB_CHECK_LAUNCH();
+  return SPB_OK;
+}
+
+// One launch for a batch (export.py:127-145 per image; Val_model_heatmap.py:151-155 is only valid for B = 1, the
+// batched semantics are the per-image loop): coarse NHWC [B,Hc,Wc,D], pts [B,K,3], counts [B] -> out [B,K,D], the
+// rows behind counts[b] zero filled.
+extern "C" int spb_sample_desc_batch(const float* coarse_nhwc, const float* pts, const int* counts, int B, int K, int Hc,
+                                     int Wc, int D, int cell, int normalize, float* out, void* stream) {
+  SPB_CHECK_ARG(coarse_nhwc && pts && counts && out);
+  SPB_CHECK_ARG(B >= 0 && B <= 65535 && K >= 0 && Hc >= 2 && Wc >= 2 && D >= 1 && cell >= 1);
+  if (K == 0 || B == 0) return SPB_OK;
+  dim3 grid(ceil_div(K, 8), B);
+  sample_desc_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(coarse_nhwc, pts, counts, K, Hc, Wc, D, cell, out, 3,
+                                                                normalize, 1);
   SPB_CHECK_LAUNCH();
   return SPB_OK;
 }
@@ -78,6 +102,10 @@ __global__ void __launch_bounds__(128) soft_argmax_kernel(const float* __restric
                                                           const float* __restrict__ pts, const int* __restrict__ count,
                                                           int K, int P, float* __restrict__ dxdy) {
   const int k = blockIdx.x * 128 + threadIdx.x;
+  heat += (long long)blockIdx.y * H * W;  // blockIdx.y = image of a batch: heat [B,H,W], pts [B,K,3], dxdy [B,K,2]
+  pts += (long long)blockIdx.y * K * 3;
+  dxdy += (long long)blockIdx.y * K * 2;
+  if (count) count += blockIdx.y;
   const int n = count ? min(*count, K) : K;
   if (k >= n) return;
   const int x0 = (int)pts[3 * k] - P / 2, y0 = (int)pts[3 * k + 1] - P / 2;
@@ -116,6 +144,18 @@ extern "C" int spb_soft_argmax_points(const float* heat, int H, int W, const flo
   if (K == 0) return SPB_OK;
   spb::soft_argmax_kernel<<<spb::ceil_div(K, 128), 128, 0, spb::as_stream(stream)>>>(heat, H, W, pts, count, K,
                                                                                      patch_size, dxdy);
+  SPB_CHECK_LAUNCH();
+  return SPB_OK;
+}
+
+// The same for a batch in one launch: heat [B,H,W], pts [B,K,3], counts [B] (device), dxdy [B,K,2].
+extern "C" int spb_soft_argmax_points_batch(const float* heat, int B, int H, int W, const float* pts, const int* counts,
+                                            int K, int patch_size, float* dxdy, void* stream) {
+  SPB_CHECK_ARG(heat && pts && counts && dxdy && H > 0 && W > 0 && K >= 0 && B >= 0 && B <= 65535);
+  SPB_CHECK_ARG(patch_size >= 1 && patch_size <= 7 && (patch_size & 1));
+  if (K == 0 || B == 0) return SPB_OK;
+  dim3 grid(spb::ceil_div(K, 128), B);
+  spb::soft_argmax_kernel<<<grid, 128, 0, spb::as_stream(stream)>>>(heat, H, W, pts, counts, K, patch_size, dxdy);
   SPB_CHECK_LAUNCH();
   return SPB_OK;
 }

@@ -8,7 +8,7 @@
 // views are split into G groups over blockIdx.y; each CTA accumulates its views in registers in
 // a fixed order and writes one partial; a second tiny kernel adds the G partials in order, so the
 // result is deterministic (no atomics).  HBM traffic: N*65*Hc*Wc*4 B read once + 2*H*W*4*(G+1).
-#include "common.cuh"
+#include "net.cuh"
 
 namespace spb {
 
@@ -222,35 +222,30 @@ __global__ void __launch_bounds__(256) ha_aggregate_kernel(AggParams p) {
   }
 }
 
-// HA product path: the detector head's epilogue already wrote softmax probabilities (dustbin dropped) as
-// probs[N,Hc,Wc,64] and the warp kernel wrote the valid-mask bits, so aggregation is a pure gather:
-// one thread per output pixel, views n = g, g+G, ... accumulated in registers in a fixed order.
-// blockIdx.z = image * G + group; image b owns views [b*N, (b+1)*N) of probs / bits.
-// offs != NULL (balanced homography sharding): image b owns the views [offs[b], offs[b+1]) of the flat view list,
-// probs / bits / mu are indexed by the flat view number.
+// Bit-exact gather form of the aggregate (validation path SPB_IMPL_SIMT; the product path is ha_fast.cu): softmax
+// probabilities (dustbin dropped) as probs[V,Hc,Wc,64] and the valid-mask bits of the warped views,
+// one thread per output pixel, views n = begin + g, begin + g + G, ... accumulated in registers in a fixed order.
+// blockIdx.z = image * G + group; image b owns the views [b*N, (b+1)*N) of the pass, or [offs[b], offs[b+1]) when
+// offs != NULL (homography sharding: a different number of views per image); view n uses the matrix vm.mat(n).
 __global__ void __launch_bounds__(256) agg_probs_kernel(const float* __restrict__ probs,
                                                         const uint8_t* __restrict__ bits,
-                                                        const float* __restrict__ mu, int shared_mats, int N, int H,
+                                                        const float* __restrict__ mu, ViewMap vm, int N, int H,
                                                         int W, int G, float* __restrict__ part, Lin lx, Lin ly,
                                                         const int* __restrict__ offs) {
   const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
   if (x >= W || y >= H) return;
   const int Wc = W >> 3, Hc = H >> 3;
   const int b = blockIdx.z / G, g = blockIdx.z % G;
-  int n_begin = g, n_end = N;
+  int n_begin = b * N + g, n_end = (b + 1) * N;  // flat view numbers of the pass (probs / bits / vm index)
   if (offs) {
     n_begin = __ldg(offs + b) + g;
     n_end = __ldg(offs + b + 1);
-  } else {
-    probs += (long long)b * N * Hc * Wc * 64;
-    bits += (long long)b * N * H * Wc;
-    if (!shared_mats) mu += (long long)b * N * 9;
   }
   const float u = lx.at(x), v = ly.at(y);
   const float wm = (float)(W - 1), hm = (float)(H - 1);
   float num = 0.f, den = 0.f;
   for (int n = n_begin; n < n_end; n += G) {
-    const Mat3 M = load_mat(mu + 9 * n);
+    const Mat3 M = load_mat(mu + 9LL * vm.mat(n));
     float ix, iy;
     warp_coord(M, u, v, W, H, ix, iy);
     const Taps tp = make_taps(ix, iy);
@@ -333,17 +328,21 @@ size_t aggregate_probs_workspace(int B, int N, int H, int W) {
 }
 
 // B images x N views each (probs / bits contiguous over b*N + n); sums [B,2,H,W]
-int aggregate_probs(const float* probs, const uint8_t* bits, const float* mats_unwarp, int shared_mats, int B, int N,
+int reduce_partials(const float* part, int G, int nb, int H, int W, float* sums, int accumulate, cudaStream_t st) {
+  const long long n = 2LL * H * W, total = n * nb;
+  agg_reduce_kernel<<<min(ceil_div(total, 256), kNumSMs * 8), 256, 0, st>>>(part, G, n, total, sums, accumulate);
+  SPB_CHECK_LAUNCH();
+  return SPB_OK;
+}
+
+int aggregate_probs(const float* probs, const uint8_t* bits, const float* mats_unwarp, const ViewMap& vm, int B, int N,
                     int H, int W, float* sums, int accumulate, void* ws, cudaStream_t st, const int* offs) {
   const int G = aggregate_probs_groups(B, N, H, W);  // (ragged: N = the largest per-image view count)
   float* part = static_cast<float*>(ws);
   dim3 grid(ceil_div(W, 32), ceil_div(H, 8), G * B);
-  agg_probs_kernel<<<grid, 256, 0, st>>>(probs, bits, mats_unwarp, shared_mats, N, H, W, G, part, Lin(W), Lin(H), offs);
+  agg_probs_kernel<<<grid, 256, 0, st>>>(probs, bits, mats_unwarp, vm, N, H, W, G, part, Lin(W), Lin(H), offs);
   SPB_CHECK_LAUNCH();
-  const long long n = 2LL * H * W, total = n * B;
-  agg_reduce_kernel<<<min(ceil_div(total, 256), kNumSMs * 8), 256, 0, st>>>(part, G, n, total, sums, accumulate);
-  SPB_CHECK_LAUNCH();
-  return SPB_OK;
+  return reduce_partials(part, G, B, H, W, sums, accumulate, st);
 }
 
 }  // namespace spb

@@ -23,11 +23,23 @@ static inline void* align_ptr(void* p) {  // workspaces carry 1 KB of slack for 
   return reinterpret_cast<void*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~(uintptr_t)1023);
 }
 
+// The workspace-size entry points take no network handle, so the layout cannot depend on a net's implementation
+// switch: once any net of the process has been put on the CUDA-core validation path (which runs conv1a and conv1b
+// as two kernels and needs the full-resolution intermediate), every workspace is sized for it.
+static bool g_simt_used = false;
+static inline bool first_block_fused(int H, int W) {
+  return !g_simt_used && conv1_fused_enabled() && conv1_fused_supports(H, W);
+}
+
 struct Workspace {  // carve-up of the caller's buffer for a batch of B views at H x W
   __nv_bfloat16 *buf0, *buf1;
   size_t bytes;
   Workspace(void* base, int B, int H, int W) {
-    const size_t b0 = align_up((size_t)B * H * W * 64 * 2, 1024);
+    // buf0 holds conv1a's full-resolution output only when the first block runs as two kernels; with the fused
+    // block (the default) its largest tenant is conv2a's H/2 x W/2 output -- 4x smaller (800 views at 240x320:
+    // 2 GB instead of 7.9 GB)
+    const size_t full = first_block_fused(H, W) ? (size_t)(H / 2) * (W / 2) : (size_t)H * W;
+    const size_t b0 = align_up((size_t)B * full * 64 * 2, 1024);
     const size_t b1 = align_up((size_t)B * (H / 2) * (W / 2) * 64 * 2, 1024);
     char* p = static_cast<char*>(base);
     buf0 = reinterpret_cast<__nv_bfloat16*>(p);
@@ -98,14 +110,15 @@ static int run_layer(const Net* net, int li, const void* in, void* out, int B, i
   return rc;
 }
 
-// semi: logits [B,Hc,Wc,65] (or NULL); probs: softmax probabilities [B,Hc,Wc,64] (or NULL); desc optional
+// semi: logits [B,Hc,Wc,65] (or NULL); probs: softmax probabilities [B,Hc,Wc,64] (or NULL); desc optional;
+// heat16 (+ bits): fp16 probability planes of the HA pass (conv_tc out_mode 4), tcgen05 only
 static int forward(const Net* net, const float* x, int B, int H, int W, float* semi, float* probs, float* desc,
-                   void* ws, cudaStream_t st) {
+                   void* ws, cudaStream_t st, void* heat16 = nullptr, const uint8_t* bits = nullptr) {
   Workspace w(ws, B, H, W);
   int rc;
 #define RUN(li, in, out, h, wd, mode)                                     \
   if ((rc = run_layer(net, li, in, out, B, h, wd, mode, st)) != SPB_OK) return rc
-  if (net->impl == SPB_IMPL_TCGEN05 && conv1_fused_enabled() && conv1_fused_supports(H, W)) {
+  if (net->impl == SPB_IMPL_TCGEN05 && first_block_fused(H, W)) {
     // conv1a + conv1b + pool in one kernel: the 64-channel full-resolution activation never leaves the SM
     StageTimer tm(net, 1, st);
     if ((rc = conv1_fused(net->layer[0], net->layer[1], x, w.buf1, B, H, W, st)) != SPB_OK) return rc;
@@ -133,6 +146,14 @@ static int forward(const Net* net, const float* x, int B, int H, int W, float* s
       softmax_rows_kernel<<<min(ceil_div(rows, 8), kNumSMs * 8), 256, 0, st>>>(semi, probs, rows);
       SPB_CHECK_LAUNCH();
     }
+  }
+  if (heat16) {
+    if (net->impl != SPB_IMPL_TCGEN05 || !bits) {
+      set_error("forward: fp16 probability planes are produced by the tcgen05 path only");
+      return SPB_EINVAL;
+    }
+    StageTimer tm(net, 9, st);
+    if ((rc = conv_tc(net->layer[9], w.buf0, heat16, B, H / 8, W / 8, 4, st, bits)) != SPB_OK) return rc;
   }
   if (desc) {
     RUN(10, w.buf1, w.buf0, H / 8, W / 8, 0);
@@ -262,6 +283,7 @@ int spb_net_destroy(spb_net* h) {
 
 int spb_net_set_impl(spb_net* h, int impl) {
   SPB_CHECK_ARG(h && (impl == SPB_IMPL_TCGEN05 || impl == SPB_IMPL_SIMT));
+  if (impl == SPB_IMPL_SIMT) g_simt_used = true;  // (sticky: see first_block_fused)
   reinterpret_cast<Net*>(h)->impl = impl;
   return SPB_OK;
 }
@@ -291,36 +313,55 @@ int spb_net_layer(spb_net* h, int layer, const void* in, void* out, int B, int H
 }
 
 // ---- whole HA step ----------------------------------------------------------------------------------
-// One pass = Bg images x n views each through warp -> detector net -> gather-aggregate.
+// One pass = V views (nb images) through: prep -> warp (+ mask bits) -> detector net -> gather-aggregate.
+// tcgen05 (product): ha_fast.cu kernels, the detector head writes masked fp16 probability planes.
+// SIMT (validation): the bit-exact CUDA-core warp / aggregate kernels around logits + a softmax kernel.
 struct HaLayout {
-  size_t warp, bits, semi, probs, agg, net, warp2, bits2, total;  // warp2 / bits2: second pass buffer (overlap mode)
+  size_t warp, bits, semi, probs, agg, net, warp2, bits2, src_pad, fold, total;
 };
-static HaLayout ha_layout(int Bg, int n, int H, int W) {
-  const size_t V = (size_t)Bg * n, cells = (size_t)(H / 8) * (W / 8);
+static size_t heat16_bytes(size_t V, int H, int W) {
+  return V * (size_t)(H + 2 * kHeatPadY) * (size_t)(W + 2 * kHeatPadX) * 2;
+}
+// V views of nb images (at most max_views per image); two = a second set of warp / bits / probability buffers
+// (overlapped passes of spb_ha_heatmap_sums_batch)
+static HaLayout ha_layout(int nb, size_t V, int max_views, int H, int W, bool simt, bool two) {
+  const size_t cells = (size_t)(H / 8) * (W / 8);
   HaLayout L;
   size_t o = 0;
   L.warp = o;
   o += align_up(V * H * W * 4, 1024);
   L.bits = o;
   o += align_up(V * H * (W / 8), 1024);
-  L.semi = o;  // logits: SIMT validation path only
-  o += align_up(V * cells * 65 * 4, 1024);
-  L.probs = o;
-  o += align_up(V * cells * 64 * 4, 1024);
+  L.semi = o;  // logits (SIMT validation path) / second probability buffer (overlapped passes)
+  o += (simt || two) ? align_up(simt ? V * cells * 65 * 4 : heat16_bytes(V, H, W), 1024) : 0;
+  L.probs = o;  // fp32 [V,cells,64] (SIMT) or the fp16 planes (tcgen05)
+  o += align_up(simt ? V * cells * 64 * 4 : heat16_bytes(V, H, W), 1024);
   L.agg = o;
-  o += align_up(aggregate_probs_workspace(Bg, n, H, W), 1024);
+  o += align_up(aggregate_probs_workspace(nb, max_views, H, W), 1024);
   L.net = o;
   o += spb_net_workspace_bytes((int)V, H, W, 0);
   L.warp2 = o;
-  o += align_up(V * H * W * 4, 1024);
+  o += two ? align_up(V * H * W * 4, 1024) : 0;
   L.bits2 = o;
-  o += align_up(V * H * (W / 8), 1024);
+  o += two ? align_up(V * H * (W / 8), 1024) : 0;
+  L.src_pad = o;
+  o += align_up((size_t)nb * (H + 2 * kHaPad) * (W + 2 * kHaPad) * 4, 1024);
+  L.fold = o;  // [2 sets][2][V] FoldMat
+  o += align_up(4 * V * sizeof(FoldMat), 1024);
   L.total = o + 1024;
   return L;
 }
 
-static void ha_plan(const Net* net, int B, int N, int& Bg, int& n) {
-  const int cap = net->ha_chunk > 0 ? net->ha_chunk : 800;  // views per pass
+// Views per pass: bounded by BYTES (views x H x W), not by a count -- 800 views at 240x320 (61 M pixels: 0.25 GB of
+// fp32 views + 2 GB of half-resolution bf16 activations), 200 at 480x640, 128 at 384x1248.
+static int ha_pass_views(const Net* net, int H, int W) {
+  if (net && net->ha_chunk > 0) return net->ha_chunk;
+  const long long cap = 800LL * 240 * 320 / ((long long)H * W);
+  return cap < 1 ? 1 : (int)cap;
+}
+
+static void ha_plan(const Net* net, int B, int N, int H, int W, int& Bg, int& n) {
+  const int cap = ha_pass_views(net, H, W);
   if (cap >= N) {
     n = N;
     Bg = cap / N;
@@ -331,16 +372,61 @@ static void ha_plan(const Net* net, int B, int N, int& Bg, int& n) {
   }
 }
 
+struct PassBufs {
+  float* warped;
+  uint8_t* bits;
+  void* probs;     // fp16 planes (tcgen05) or fp32 [V,cells,64] (SIMT)
+  float* semi;     // SIMT only
+  FoldMat* fold;   // [2][V]: forward, un-warp
+  float* src_pad;
+  void* agg_ws;
+  void* net_ws;
+};
+
+// imgs: first image of the pass; mats_*: the arrays vm.mat() indexes; offs: NULL (nb x n views) or device int[nb+1]
+static int ha_warp_stage(Net* net, const PassBufs& pb, const float* imgs, const float* mats_unwarp,
+                         const float* mats_fwd, const ViewMap& vm, int nb, int V, int H, int W, cudaStream_t st) {
+  int rc;
+  if (net->impl == SPB_IMPL_TCGEN05) {
+    StageTimer tm(net, 12, st);
+    rc = ha_prep(imgs, pb.src_pad, mats_fwd, mats_unwarp, pb.fold, pb.fold + V, pb.probs, vm, nb, V, H, W, st);
+    if (rc != SPB_OK) return rc;
+    return warp_views(pb.src_pad, pb.fold, mats_fwd, pb.warped, pb.bits, vm, V, H, W, st);
+  }
+  StageTimer tm(net, 12, st);
+  return warp_with_mask_bits(imgs, mats_fwd, pb.warped, pb.bits, V, vm, H, W, st);
+}
+static int ha_net_stage(Net* net, const PassBufs& pb, int V, int H, int W, cudaStream_t st) {
+  if (net->impl == SPB_IMPL_TCGEN05)
+    return forward(net, pb.warped, V, H, W, nullptr, nullptr, nullptr, pb.net_ws, st, pb.probs, pb.bits);
+  return forward(net, pb.warped, V, H, W, pb.semi, static_cast<float*>(pb.probs), nullptr, pb.net_ws, st);
+}
+static int ha_agg_stage(Net* net, const PassBufs& pb, const float* mats_unwarp, const ViewMap& vm, int nb,
+                        int max_views, int V, int H, int W, float* sums, int accumulate, const int* offs,
+                        cudaStream_t st) {
+  StageTimer tm(net, 13, st);
+  if (net->impl == SPB_IMPL_TCGEN05)
+    return aggregate_heat16(pb.probs, pb.fold + V, nb, max_views, H, W, sums, accumulate, pb.agg_ws, st, offs);
+  return aggregate_probs(static_cast<const float*>(pb.probs), pb.bits, mats_unwarp, vm, nb, max_views, H, W, sums,
+                         accumulate, pb.agg_ws, st, offs);
+}
+
 size_t spb_ha_workspace_bytes_batch(spb_net* h, int B, int N, int H, int W) {
   if (!h || B < 1 || N < 1 || H < 8 || W < 8) return 0;
+  Net* net = reinterpret_cast<Net*>(h);
   int Bg, n;
-  ha_plan(reinterpret_cast<Net*>(h), B, N, Bg, n);
-  return ha_layout(Bg, n, H, W).total;
+  ha_plan(net, B, N, H, W, Bg, n);
+  return ha_layout(Bg, (size_t)Bg * n, n, H, W, net->impl != SPB_IMPL_TCGEN05, net->ha_overlap != 0).total;
 }
 
 size_t spb_ha_workspace_bytes(int N, int H, int W) {
   if (N < 1 || H < 8 || W < 8) return 0;
-  return ha_layout(1, N, H, W).total;  // an upper bound for every chunk setting of a single image
+  return ha_layout(1, (size_t)N, N, H, W, true, true).total;  // an upper bound for every setting of a single image
+}
+
+int spb_ha_pass_views(spb_net* h, int H, int W) {
+  if (H < 8 || W < 8) return 0;
+  return ha_pass_views(reinterpret_cast<Net*>(h), H, W);
 }
 
 int spb_ha_heatmap_sums_batch(spb_net* h, const float* imgs, const float* mats_unwarp, const float* mats_fwd,
@@ -350,15 +436,14 @@ int spb_ha_heatmap_sums_batch(spb_net* h, const float* imgs, const float* mats_u
   SPB_CHECK_ARG(B >= 1 && N >= 1 && H >= 8 && W >= 8 && H % 8 == 0 && W % 8 == 0);
   Net* net = reinterpret_cast<Net*>(h);
   int Bg, n;
-  ha_plan(net, B, N, Bg, n);
-  const HaLayout L = ha_layout(Bg, n, H, W);
+  ha_plan(net, B, N, H, W, Bg, n);
+  const bool tc = net->impl == SPB_IMPL_TCGEN05;
+  const HaLayout L = ha_layout(Bg, (size_t)Bg * n, n, H, W, !tc, net->ha_overlap != 0);
   if (ws_bytes < L.total) {
     set_error("spb_ha_heatmap_sums: workspace %zu < %zu bytes", ws_bytes, L.total);
     return SPB_ENOMEM;
   }
   char* base = static_cast<char*>(align_ptr(ws));
-  float* semi = reinterpret_cast<float*>(base + L.semi);
-  const bool tc = net->impl == SPB_IMPL_TCGEN05;
   cudaStream_t st = as_stream(stream);
   // the passes: Bg images x n views each (view chunks of ONE image only when it has more views than a pass holds;
   // per-image matrix sets are only contiguous over a whole image, so view chunks imply bg == 1)
@@ -375,41 +460,54 @@ int spb_ha_heatmap_sums_batch(spb_net* h, const float* imgs, const float* mats_u
     return p;
   };
   auto moff = [&](const Pass& p) { return shared_mats ? 9LL * p.n0 : 9LL * ((long long)p.b0 * N + p.n0); };
-  // pass buffers: [c & 1]; the logits region of the SIMT validation path doubles as the second probability buffer
-  float* warped[2] = {reinterpret_cast<float*>(base + L.warp), reinterpret_cast<float*>(base + L.warp2)};
-  uint8_t* bits[2] = {reinterpret_cast<uint8_t*>(base + L.bits), reinterpret_cast<uint8_t*>(base + L.bits2)};
-  float* probs[2] = {reinterpret_cast<float*>(base + L.probs), semi};
+  const size_t Vmax = (size_t)Bg * n;
+  auto bufs = [&](int c) {  // pass buffers alternate by pass parity in the overlapped mode
+    const int k = (net->ha_overlap && tc) ? (c & 1) : 0;
+    PassBufs pb;
+    pb.warped = reinterpret_cast<float*>(base + (k ? L.warp2 : L.warp));
+    pb.bits = reinterpret_cast<uint8_t*>(base + (k ? L.bits2 : L.bits));
+    pb.probs = base + ((k && tc) ? L.semi : L.probs);
+    pb.semi = reinterpret_cast<float*>(base + L.semi);
+    pb.fold = reinterpret_cast<FoldMat*>(base + L.fold) + (size_t)k * 2 * Vmax;
+    pb.src_pad = reinterpret_cast<float*>(base + L.src_pad);
+    pb.agg_ws = base + L.agg;
+    pb.net_ws = base + L.net;
+    return pb;
+  };
+  auto vmap = [&](const Pass& p) {
+    ViewMap vm;
+    vm.view_image = nullptr;
+    vm.view_mat = nullptr;
+    vm.vpi = p.nn;
+    vm.shared = shared_mats;
+    return vm;
+  };
   auto do_warp = [&](int c, cudaStream_t s) {
     const Pass p = pass(c);
-    StageTimer tm(net, 12, s);
-    return warp_with_mask_bits(imgs + (long long)p.b0 * H * W, mats_fwd + moff(p), warped[c & 1], bits[c & 1],
-                               p.bg * p.nn, p.nn, shared_mats, nullptr, H, W, s);
+    return ha_warp_stage(net, bufs(c), imgs + (long long)p.b0 * H * W, mats_unwarp + moff(p), mats_fwd + moff(p),
+                         vmap(p), p.bg, p.bg * p.nn, H, W, s);
   };
-  auto do_agg = [&](int c, int buf, cudaStream_t s) {
+  auto do_agg = [&](int c, cudaStream_t s) {
     const Pass p = pass(c);
-    StageTimer tm(net, 13, s);
-    return aggregate_probs(probs[buf], bits[c & 1], mats_unwarp + moff(p), shared_mats, p.bg, p.nn, H, W,
-                           sums + (long long)p.b0 * 2 * H * W, accumulate || p.n0 > 0, base + L.agg, s);
+    return ha_agg_stage(net, bufs(c), mats_unwarp + moff(p), vmap(p), p.bg, p.nn, p.bg * p.nn, H, W,
+                        sums + (long long)p.b0 * 2 * H * W, accumulate || p.n0 > 0, nullptr, s);
   };
   int rc;
   if (!(tc && net->ha_overlap && P > 1)) {
     for (int c = 0; c < P; ++c) {
       const Pass p = pass(c);
       if ((rc = do_warp(c, st)) != SPB_OK) return rc;
-      // the detector head writes softmax probabilities directly (tcgen05 epilogue); the validation path goes
-      // through logits + a softmax kernel
-      rc = forward(net, warped[c & 1], p.bg * p.nn, H, W, tc ? nullptr : semi, probs[0], nullptr, base + L.net, st);
-      if (rc != SPB_OK) return rc;
-      if ((rc = do_agg(c, 0, st)) != SPB_OK) return rc;
+      if ((rc = ha_net_stage(net, bufs(c), p.bg * p.nn, H, W, st)) != SPB_OK) return rc;
+      if ((rc = do_agg(c, st)) != SPB_OK) return rc;
     }
     return SPB_OK;
   }
-  // Overlapped passes (opt-in, spb_net_set_ha_overlap): the image warp and the aggregate are instruction-bound
-  // gathers that leave the tensor cores idle (8 % of a pass), and a 256-thread CTA of either fits into the registers
-  // the persistent conv kernels leave free on every SM.  Measured on the 32-image bench step: 861 vs 848 images/s
-  // (within the run-to-run spread; the part is power capped, so hiding time does not buy energy) while conv1's own
-  // launches get 6 % longer -- off by default.  Side stream:  warp(1) | agg(0) warp(2) | agg(1) warp(3) | ...   main stream: warp(0), then
-  // the detector net of every pass.  Buffers alternate by pass parity; the hazards are
+  // Overlapped passes (opt-in, spb_net_set_ha_overlap): the image warp and the aggregate leave the tensor cores
+  // idle, and a 256-thread CTA of either fits into the registers the persistent conv kernels leave free on every SM.
+  // Measured in round 1: +1.5 % at best under the power cap -- off by default.
+  // Side stream:  warp(1) | agg(0) warp(2) | agg(1) warp(3) | ...   main stream: warp(0), then the detector net of
+  // every pass.  Buffers alternate by pass parity (the padded source images are shared: the side stream is ordered,
+  // and the main stream's only use of them is warp(0) before anything else); the hazards are
   //   net(c)    after warp(c)                      (ev_warp)    and after agg(c-2) released probs[c&1]   (ev_agg)
   //   agg(c)    after net(c)                       (ev_fwd)
   //   warp(c+2) after net(c) read warped[c&1] and agg(c) read bits[c&1]   (side-stream order behind agg(c))
@@ -424,20 +522,19 @@ int spb_ha_heatmap_sums_batch(spb_net* h, const float* imgs, const float* mats_u
     }
   }
   cudaStream_t sx = net->aux;
-  SPB_CHECK_CUDA(cudaEventRecord(net->ev_begin, st));  // everything the caller queued before this call
-  SPB_CHECK_CUDA(cudaStreamWaitEvent(sx, net->ev_begin, 0));
   if ((rc = do_warp(0, st)) != SPB_OK) return rc;
+  SPB_CHECK_CUDA(cudaEventRecord(net->ev_begin, st));  // everything the caller queued before this call + warp(0)
+  SPB_CHECK_CUDA(cudaStreamWaitEvent(sx, net->ev_begin, 0));
   if ((rc = do_warp(1, sx)) != SPB_OK) return rc;
   SPB_CHECK_CUDA(cudaEventRecord(net->ev_warp[1], sx));
   for (int c = 0; c < P; ++c) {
     const Pass p = pass(c);
     if (c >= 1) SPB_CHECK_CUDA(cudaStreamWaitEvent(st, net->ev_warp[c & 1], 0));
     if (c >= 2) SPB_CHECK_CUDA(cudaStreamWaitEvent(st, net->ev_agg[c & 1], 0));
-    rc = forward(net, warped[c & 1], p.bg * p.nn, H, W, nullptr, probs[c & 1], nullptr, base + L.net, st);
-    if (rc != SPB_OK) return rc;
+    if ((rc = ha_net_stage(net, bufs(c), p.bg * p.nn, H, W, st)) != SPB_OK) return rc;
     SPB_CHECK_CUDA(cudaEventRecord(net->ev_fwd[c & 1], st));
     SPB_CHECK_CUDA(cudaStreamWaitEvent(sx, net->ev_fwd[c & 1], 0));
-    if ((rc = do_agg(c, c & 1, sx)) != SPB_OK) return rc;
+    if ((rc = do_agg(c, sx)) != SPB_OK) return rc;
     SPB_CHECK_CUDA(cudaEventRecord(net->ev_agg[c & 1], sx));
     if (c + 2 < P) {
       if ((rc = do_warp(c + 2, sx)) != SPB_OK) return rc;
@@ -448,16 +545,17 @@ int spb_ha_heatmap_sums_batch(spb_net* h, const float* imgs, const float* mats_u
   return SPB_OK;
 }
 
-// Balanced homography sharding: a flat list of V views with a different number of views per image.
+// Homography sharding: a flat list of V views with a different number of views per image and explicit matrix
+// indices (ONE pass: the caller cuts a batch into passes of at most spb_ha_pass_views views, sharding.plan_batch).
 size_t spb_ha_workspace_bytes_ragged(int B, int V, int max_views_per_image, int H, int W) {
   if (B < 1 || V < 1 || max_views_per_image < 1 || H < 8 || W < 8) return 0;
-  HaLayout L = ha_layout(1, V, H, W);
-  return L.total + align_up(aggregate_probs_workspace(B, max_views_per_image, H, W), 1024);
+  return ha_layout(B, (size_t)V, max_views_per_image, H, W, false, false).total;
 }
 
 int spb_ha_heatmap_sums_ragged(spb_net* h, const float* imgs, const float* mats_unwarp, const float* mats_fwd,
-                               const int* view_image, const int* view_offsets, int B, int V, int max_views_per_image,
-                               int H, int W, float* sums, int accumulate, void* ws, size_t ws_bytes, void* stream) {
+                               const int* view_image, const int* view_mat, const int* view_offsets, int B, int V,
+                               int max_views_per_image, int H, int W, float* sums, int accumulate, void* ws,
+                               size_t ws_bytes, void* stream) {
   SPB_CHECK_ARG(h && imgs && mats_unwarp && mats_fwd && view_image && view_offsets && sums && ws);
   SPB_CHECK_ARG(B >= 1 && V >= 1 && max_views_per_image >= 1 && H >= 8 && W >= 8 && H % 8 == 0 && W % 8 == 0);
   Net* net = reinterpret_cast<Net*>(h);
@@ -470,27 +568,60 @@ int spb_ha_heatmap_sums_ragged(spb_net* h, const float* imgs, const float* mats_
               spb_ha_workspace_bytes_ragged(B, V, max_views_per_image, H, W));
     return SPB_ENOMEM;
   }
-  const HaLayout L = ha_layout(1, V, H, W);
+  const HaLayout L = ha_layout(B, (size_t)V, max_views_per_image, H, W, false, false);
   char* base = static_cast<char*>(align_ptr(ws));
-  float* warped = reinterpret_cast<float*>(base + L.warp);
-  uint8_t* bits = reinterpret_cast<uint8_t*>(base + L.bits);
-  float* probs = reinterpret_cast<float*>(base + L.probs);
-  char* agg_ws = base + L.total - 1024;  // the aggregate's partial sums live behind the single-image layout
+  PassBufs pb;
+  pb.warped = reinterpret_cast<float*>(base + L.warp);
+  pb.bits = reinterpret_cast<uint8_t*>(base + L.bits);
+  pb.probs = base + L.probs;
+  pb.semi = nullptr;
+  pb.fold = reinterpret_cast<FoldMat*>(base + L.fold);
+  pb.src_pad = reinterpret_cast<float*>(base + L.src_pad);
+  pb.agg_ws = base + L.agg;
+  pb.net_ws = base + L.net;
+  ViewMap vm;
+  vm.view_image = view_image;
+  vm.view_mat = view_mat;  // NULL: the matrices are listed in view order
+  vm.vpi = 1;
+  vm.shared = 0;
   cudaStream_t st = as_stream(stream);
   int rc;
-  {
-    StageTimer tm(net, 12, st);
-    rc = warp_with_mask_bits(imgs, mats_fwd, warped, bits, V, 1, 0, view_image, H, W, st);
+  if ((rc = ha_warp_stage(net, pb, imgs, mats_unwarp, mats_fwd, vm, B, V, H, W, st)) != SPB_OK) return rc;
+  if ((rc = ha_net_stage(net, pb, V, H, W, st)) != SPB_OK) return rc;
+  return ha_agg_stage(net, pb, mats_unwarp, vm, B, max_views_per_image, V, H, W, sums, accumulate, view_offsets, st);
+}
+
+// The image side of the HA branch on its own (datasets/Coco.py:279-282): V warped views + their valid-mask bits with
+// the kernels of the fused pass (folded coordinates: views within ~1e-3 of spb_inv_warp_image_batch, mask bits exact).
+size_t spb_ha_warp_views_workspace_bytes(int nb, int V, int H, int W) {
+  if (nb < 1 || V < 1 || H < 8 || W < 8) return 0;
+  return align_up((size_t)nb * (H + 2 * kHaPad) * (W + 2 * kHaPad) * 4, 1024) + align_up(2 * (size_t)V * sizeof(FoldMat), 1024) +
+         align_up(heat16_bytes(1, H, W), 1024) + 1024;
+}
+
+int spb_ha_warp_views(const float* imgs, const float* mats_fwd, const int* view_image, const int* view_mat, int nb,
+                      int V, int H, int W, float* views, uint8_t* bits, void* ws, size_t ws_bytes, void* stream) {
+  SPB_CHECK_ARG(imgs && mats_fwd && view_image && views && bits && ws);
+  SPB_CHECK_ARG(nb >= 1 && V >= 1 && H >= 8 && W >= 8 && W % 8 == 0);
+  if (ws_bytes < spb_ha_warp_views_workspace_bytes(nb, V, H, W)) {
+    set_error("spb_ha_warp_views: workspace %zu < %zu bytes", ws_bytes, spb_ha_warp_views_workspace_bytes(nb, V, H, W));
+    return SPB_ENOMEM;
   }
+  char* base = static_cast<char*>(align_ptr(ws));
+  float* src_pad = reinterpret_cast<float*>(base);
+  base += align_up((size_t)nb * (H + 2 * kHaPad) * (W + 2 * kHaPad) * 4, 1024);
+  FoldMat* fold = reinterpret_cast<FoldMat*>(base);
+  base += align_up(2 * (size_t)V * sizeof(FoldMat), 1024);
+  ViewMap vm;
+  vm.view_image = view_image;
+  vm.view_mat = view_mat;
+  vm.vpi = 1;
+  vm.shared = 0;
+  cudaStream_t st = as_stream(stream);
+  // (the un-warp fold and the plane border of ha_prep are not needed here: V = 0 planes, forward matrices twice)
+  int rc = ha_prep(imgs, src_pad, mats_fwd, mats_fwd, fold, fold + V, base, vm, nb, V, H, W, st, /*planes=*/0);
   if (rc != SPB_OK) return rc;
-  rc = forward(net, warped, V, H, W, nullptr, probs, nullptr, base + L.net, st);
-  if (rc != SPB_OK) return rc;
-  {
-    StageTimer tm(net, 13, st);
-    rc = aggregate_probs(probs, bits, mats_unwarp, 0, B, max_views_per_image, H, W, sums, accumulate, agg_ws, st,
-                         view_offsets);
-  }
-  return rc;
+  return warp_views(src_pad, fold, mats_fwd, views, bits, vm, V, H, W, st);
 }
 
 int spb_ha_heatmap_sums(spb_net* h, const float* img, const float* mats_unwarp, const float* mats_fwd, int N, int H,

@@ -44,12 +44,23 @@ int conv1a_simt(const LayerDev& L, const float* x, __nv_bfloat16* out, int B, in
 int conv_simt(const LayerDev& L, const __nv_bfloat16* in, void* out, int B, int H, int W, int out_f32, cudaStream_t st);
 int l2norm_rows(float* d, long long rows, int C, cudaStream_t st);
 
-// warp.cu / heat.cu pieces used by the fused HA path
-int warp_with_mask_bits(const float* img, const float* mats, float* out, uint8_t* bits, int N, int vpi,
-                        int shared_mats, const int* view_img, int H, int W, cudaStream_t st);
+// warp.cu / heat.cu pieces used by the fused HA path (CUDA-core validation path, SPB_IMPL_SIMT)
+int warp_with_mask_bits(const float* img, const float* mats, float* out, uint8_t* bits, int N, const ViewMap& vm,
+                        int H, int W, cudaStream_t st);
+int aggregate_probs_groups(int B, int N, int H, int W);
 size_t aggregate_probs_workspace(int B, int N, int H, int W);
-int aggregate_probs(const float* probs, const uint8_t* bits, const float* mats_unwarp, int shared_mats, int B, int N,
+int aggregate_probs(const float* probs, const uint8_t* bits, const float* mats_unwarp, const ViewMap& vm, int B, int N,
                     int H, int W, float* sums, int accumulate, void* ws, cudaStream_t st, const int* offs = nullptr);
+int reduce_partials(const float* part, int G, int nb, int H, int W, float* sums, int accumulate, cudaStream_t st);
+
+// ha_fast.cu: the non-tensor kernels of the tcgen05 HA pass (folded homographies, padded frames, fp16 planes)
+int ha_prep(const float* imgs, float* src_pad, const float* mats_fwd, const float* mats_unwarp, FoldMat* fold_fwd,
+            FoldMat* fold_unwarp, void* heat16, const ViewMap& vm, int nb, int V, int H, int W, cudaStream_t st,
+            int planes = -1);
+int warp_views(const float* src_pad, const FoldMat* fold, const float* mats_fwd, float* out, uint8_t* bits,
+               const ViewMap& vm, int V, int H, int W, cudaStream_t st);
+int aggregate_heat16(const void* heat16, const FoldMat* fold_unwarp, int nb, int N, int H, int W, float* sums,
+                     int accumulate, void* ws, cudaStream_t st, const int* offs);
 
 // conv_tc.cu (tcgen05 / TMEM / TMA)
 int conv1a_tc(const LayerDev& L, const float* x, __nv_bfloat16* out, int B, int H, int W, cudaStream_t st);
@@ -59,8 +70,11 @@ int conv1_fused(const LayerDev& L1a, const LayerDev& L1b, const float* x, __nv_b
                 cudaStream_t st);
 int conv_tc_prepare(LayerDev& L);  // builds the weight tensor map after w_tc is uploaded
 // out_mode: 0 bf16 NHWC, 1 fp32 rows (cout channels), 2 fp32 rows L2-normalised, 3 softmax probabilities
-// (convPb only: fp32 [.,64], dustbin dropped)
-int conv_tc(const LayerDev& L, const __nv_bfloat16* in, void* out, int B, int H, int W, int out_mode, cudaStream_t st);
+// (convPb only: fp32 [.,64], dustbin dropped), 4 = convPb in the HA pass: fp16 probability planes
+// [B, 8H + 2*kHeatPadY, 8W + 2*kHeatPadX] (softmax, dustbin drop, depth-to-space; aux = the valid-mask bits
+// [B,8H,W] of the warped views: masked pixels are stored as kHeatMasked)
+int conv_tc(const LayerDev& L, const __nv_bfloat16* in, void* out, int B, int H, int W, int out_mode, cudaStream_t st,
+            const void* aux = nullptr);
 
 
 // conv_tc2.cu (CTA pairs, tcgen05.mma.cta_group::2, for the >= 128-output-channel 3x3 layers)

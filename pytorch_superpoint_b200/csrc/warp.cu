@@ -63,23 +63,21 @@ __global__ void __launch_bounds__(256) warp_kernel(const float* __restrict__ img
 // HA variant: bilinear warp of ONE image into N views + the nearest-mode valid mask of the same coordinates
 // (utils/utils.py:696 uses the same grid and matrices as the image warp, datasets/Coco.py:279-282), packed one
 // bit per pixel: bits[(n*H + y)*(W/8) + x/8] bit (x%8).  Needs W % 8 == 0.
-// View n belongs to image n / vpi; its matrix is mats[n] (per-image sets, contiguous) or mats[n % vpi] (shared).
+// View n belongs to image vm.img(n) and uses the matrix mats[vm.mat(n)] (common.cuh: ViewMap).
 // Grid: blockIdx.y = view, blockIdx.x * 256 threads over the (row, 4-pixel group) pairs of that view -- the view's
 // matrix is block-uniform and no thread divides 64-bit indices (those divisions were a quarter of the instructions).
-// view_img != NULL (balanced homography sharding: a different number of views per image): view n belongs to image
-// view_img[n] and uses mats[n].
+// This is the bit-exact CUDA-core form (validation path, SPB_IMPL_SIMT); the product path is ha_fast.cu.
 __global__ void __launch_bounds__(256) warp_bits_kernel(const float* __restrict__ img, const float* __restrict__ mats,
-                                                        float* __restrict__ out, uint8_t* __restrict__ bits, int vpi,
-                                                        int shared_mats, const int* __restrict__ view_img, int H, int W,
-                                                        Lin lx, Lin ly) {
+                                                        float* __restrict__ out, uint8_t* __restrict__ bits, ViewMap vm,
+                                                        int H, int W, Lin lx, Lin ly) {
   const unsigned Wq = (unsigned)W >> 2, per_view = (unsigned)H * Wq;
   const int lane = threadIdx.x & 31, n = blockIdx.y;
   const unsigned t = blockIdx.x * 256u + threadIdx.x;
   const bool in = t < per_view;
   const unsigned tt = in ? t : per_view - 1;
   const int y = (int)(tt / Wq), xq = (int)(tt - (unsigned)y * Wq);
-  const Mat3 M = load_mat(mats + 9 * ((shared_mats && !view_img) ? n % vpi : n));
-  const float* src = img + (long long)(view_img ? __ldg(view_img + n) : n / vpi) * H * W;
+  const Mat3 M = load_mat(mats + 9LL * vm.mat(n));
+  const float* src = img + (long long)vm.img(n) * H * W;
   const float v = ly.at(y);
   float r[4];
   unsigned nib = 0;
@@ -99,14 +97,14 @@ __global__ void __launch_bounds__(256) warp_bits_kernel(const float* __restrict_
   }
 }
 
-int warp_with_mask_bits(const float* img, const float* mats, float* out, uint8_t* bits, int N, int vpi,
-                        int shared_mats, const int* view_img, int H, int W, cudaStream_t st) {
+int warp_with_mask_bits(const float* img, const float* mats, float* out, uint8_t* bits, int N, const ViewMap& vm,
+                        int H, int W, cudaStream_t st) {
   if (N > 65535) {
     set_error("warp_with_mask_bits: %d views in one launch (max 65535)", N);
     return SPB_EINVAL;
   }
   dim3 grid(ceil_div((long long)H * (W / 4), 256), N);
-  warp_bits_kernel<<<grid, 256, 0, st>>>(img, mats, out, bits, vpi, shared_mats, view_img, H, W, Lin(W), Lin(H));
+  warp_bits_kernel<<<grid, 256, 0, st>>>(img, mats, out, bits, vm, H, W, Lin(W), Lin(H));
   SPB_CHECK_LAUNCH();
   return SPB_OK;
 }

@@ -18,17 +18,21 @@ import torch.distributed as dist
 from . import ops
 from .homographies import make_ha_homographies, sample_ha_homographies_device  # noqa: F401
 from .net import SuperPointNet_b200
-from .sharding import balanced_view_plan, owner_of_image, shard_bounds, world_info
+from .sharding import owned_images, plan_batch, sharded_heatmap_sums, world_info
 
 __all__ = ["HAExporter", "export_detector_homoAdapt_b200"]
 
 
 class HAExporter:
     """One process per GPU.  With ``torch.distributed`` initialised (NCCL) the homographies of every image are
-    sharded over the ranks and combined by a single all-reduce per batch; otherwise everything runs locally."""
+    sharded over the ranks (``sharding.plan_batch``: rotated view blocks) and combined by ONE collective per batch
+    (``sharding.exchange_sums``: a reduce-scatter over the image dimension, issued asynchronously so that it and the
+    division / NMS / top-k of batch i run under the warps and convolutions of batch i+1); otherwise everything runs
+    locally.  ``subpixel_patch`` > 0 adds the soft-argmax refinement of export.py:314-319 on the device."""
 
     def __init__(self, net: SuperPointNet_b200, conf_thresh=0.015, nms_dist=4, top_k=600, border_remove=4,
-                 device: Optional[torch.device] = None, group=None, chunk: int = 0):
+                 device: Optional[torch.device] = None, group=None, chunk: int = 0, subpixel_patch: int = 0,
+                 sharded: bool = True):
         if not torch.cuda.is_available():
             raise RuntimeError("HAExporter needs a CUDA device (sm_100a); there is no CPU fallback")
         self.net = net
@@ -36,95 +40,119 @@ class HAExporter:
         self.device = device or torch.device("cuda", torch.cuda.current_device())
         self.group = group
         self.chunk = chunk
+        self.subpixel_patch = int(subpixel_patch)
+        self.sharded = bool(sharded)  # False: ignore torch.distributed (a purely local exporter, e.g. a cross-check)
         self._bufs = {}
-        self._plan_key, self._plan = None, None
+        self._plans = {}
+        self._side = self._copy = None
 
+    def _world(self):
+        return world_info(self.group) if self.sharded else (0, 1)
+
+    # ---- buffers: everything a batch shape needs is allocated once -----------------------------------------
     def _buffers(self, B, H, W):
         key = (B, H, W)
         if key not in self._bufs:
             d1 = self.nms_dist + 1
             cap = self.top_k if self.top_k else -(-H // d1) * -(-W // d1)
             dev = self.device
-            slots = [dict(heat=torch.empty((B, H, W), device=dev, dtype=torch.float32),
-                          pts_host=torch.empty((B, cap, 3), dtype=torch.float32).pin_memory(),
-                          cnt_host=torch.empty((B,), dtype=torch.int32).pin_memory(),
-                          done=None, mine=[]) for _ in range(2)]
-            self._bufs = {key: dict(img=[torch.empty((B, H, W), device=dev, dtype=torch.float32) for _ in range(2)],
-                                    img_free=[None, None], kin=0,
-                                    sums=torch.empty((B, 2, H, W), device=dev, dtype=torch.float32),
+            rank, world = self._world()
+            lo, hi = owned_images(B, rank, world)
+            nown = max(hi - lo, 1)
+            f32 = dict(device=dev, dtype=torch.float32)
+            slots = [dict(sums=torch.empty((B, 2, H, W), **f32),        # this rank's partial planes of the batch
+                          owned=torch.empty((nown, 2, H, W), **f32),    # reduce-scatter output
+                          heat=torch.empty((nown, H, W), **f32),
+                          dxdy=torch.zeros((nown, cap, 2), **f32),
+                          pts_host=torch.empty((nown, cap, 3), dtype=torch.float32).pin_memory(),
+                          dxdy_host=torch.empty((nown, cap, 2), dtype=torch.float32).pin_memory(),
+                          cnt_host=torch.empty((nown,), dtype=torch.int32).pin_memory(),
+                          done=None, own=(lo, hi), B=B) for _ in range(2)]
+            self._bufs = {key: dict(img=[torch.empty((B, H, W), **f32) for _ in range(2)], img_free=[None, None], kin=0,
                                     slots=slots, cap=cap, k=0)}
-            self._side = torch.cuda.Stream(device=dev)
-            self._copy = torch.cuda.Stream(device=dev)
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=dev)
+                self._copy = torch.cuda.Stream(device=dev)
         return self._bufs[key]
 
-    def heatmaps(self, imgs_dev: torch.Tensor, mats_unwarp: torch.Tensor, mats_fwd: torch.Tensor,
-                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """imgs_dev [B,H,W] cuda; mats [N,3,3] (shared by the batch) or [B,N,3,3] -> aggregated heat [B,H,W]."""
-        B, H, W = imgs_dev.shape
-        buf = self._buffers(B, H, W)
-        rank, world = world_info(self.group)
-        per_image = mats_unwarp.dim() == 4
-        N = mats_unwarp.shape[-3]
-        lo, hi = shard_bounds(N, rank, world)
-        sums = buf["sums"]
-        if world > 1 and N % world and B >= world and -(-N // world) * B <= 800:
-            # uneven shares (100 views over 8 ranks = 13 or 12 per image): rotate them over the images of the batch so
-            # that every rank processes the same number of views per step (sharding.balanced_view_plan)
-            key = (B, N, rank, world)
-            if self._plan_key != key:
-                sel, vi, vo, most = balanced_view_plan(B, N, rank, world)
-                self._plan_key, self._plan = key, (sel.to(self.device), vi.to(self.device), vo.to(self.device), most)
-            sel, vi, vo, most = self._plan
-            mats_unwarp = mats_unwarp.to(self.device, torch.float32)
-            mats_fwd = mats_fwd.to(self.device, torch.float32)
-            if per_image:
-                mu, mf = mats_unwarp.reshape(B * N, 3, 3)[sel], mats_fwd.reshape(B * N, 3, 3)[sel]
-            else:
-                mu, mf = mats_unwarp[sel % N], mats_fwd[sel % N]
-            self.net.ha_heatmap_sums_ragged(imgs_dev, mu, mf, vi, vo, most, sums=sums)
-        elif hi > lo:
-            mu = mats_unwarp[:, lo:hi] if per_image else mats_unwarp[lo:hi]
-            mf = mats_fwd[:, lo:hi] if per_image else mats_fwd[lo:hi]
-            self.net.ha_heatmap_sums_batch(imgs_dev, mu, mf, sums=sums, chunk=self.chunk)
-        else:
-            sums.zero_()
-        if world > 1:
-            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=self.group)
-        # export.py:63 -- [B,2,H,W] sums -> [B,H,W] heat: one launch over the batch (sums[b,0]/sums[b,1])
-        heat = out if out is not None else buf["slots"][0]["heat"]
-        from . import _lib
-        _lib.check(_lib.lib().spb_ha_finalize_batch(sums.data_ptr(), heat.data_ptr(), B, H, W,
-                                                    torch.cuda.current_stream().cuda_stream), "ha_finalize")
-        return heat
+    def plan(self, B, N, H, W, shared: bool):
+        """The cached ``sharding.ShardPlan`` of this rank for a batch shape, its pass index arrays on the device."""
+        rank, world = self._world()
+        cap = self.chunk if self.chunk and self.chunk > 0 else self.net.ha_pass_views(H, W, self.device)
+        key = (B, N, H, W, bool(shared), rank, world, cap)
+        if key not in self._plans:
+            plan = plan_batch(B, N, rank, world, cap)
+            dev_passes = []
+            for p in plan.passes:
+                vm = p.view_mat % N if shared else p.view_mat
+                dev_passes.append((p, p.view_image.to(self.device), vm.to(self.device), p.view_offsets.to(self.device)))
+            self._plans[key] = (plan, dev_passes)
+        return self._plans[key]
+
+    def partial_sums(self, imgs_dev, mats_unwarp, mats_fwd, sums, plan_dev) -> None:
+        """This rank's partial (sum heat*mask, sum mask) planes of every image of the batch: warp -> detector
+        network -> aggregate, pass by pass (the ``partial_fn`` of ``sharding.sharded_heatmap_sums``)."""
+        mu = mats_unwarp.to(self.device, torch.float32).reshape(-1, 3, 3)
+        mf = mats_fwd.to(self.device, torch.float32).reshape(-1, 3, 3)
+        by_pass = {id(p): t for p, *t in plan_dev}
+
+        def partial_fn(p, out):
+            vi, vm, vo = by_pass[id(p)]
+            self.net.ha_heatmap_sums_ragged(imgs_dev[p.b0:p.b0 + p.nb], mu, mf, vi, vo, p.max_views,
+                                            sums=out[p.b0:p.b0 + p.nb], accumulate=p.accumulate, view_mat=vm)
+        return partial_fn
 
     def submit_resident(self, imgs_dev: torch.Tensor, mats_unwarp: torch.Tensor, mats_fwd: torch.Tensor):
-        """Device-resident inputs -> enqueue heat-maps on the current stream and NMS/top-k + the D2H of the
-        key-points on a side stream, so they overlap the next batch's convolutions.  Returns a ticket for collect()."""
+        """Device-resident inputs (imgs [B,H,W]; mats [N,3,3] shared by the batch or [B,N,3,3]) -> enqueue the
+        partial sums on the current stream, the exchange on NCCL's stream and the division + NMS / top-k + the D2H of
+        the key-points on a side stream, so they overlap the next batch's kernels.  Returns a ticket for collect()."""
         B, H, W = imgs_dev.shape
         buf = self._buffers(B, H, W)
-        rank, world = world_info(self.group)
+        shared = mats_unwarp.dim() == 3
+        N = mats_unwarp.shape[-3]
+        plan, plan_dev = self.plan(B, N, H, W, shared)
         slot = buf["slots"][buf["k"] & 1]
         buf["k"] += 1
         main = torch.cuda.current_stream()
         if slot["done"] is not None:
-            main.wait_event(slot["done"])  # the side stream still reads this slot's heat-map from two batches ago
-        heat = self.heatmaps(imgs_dev, mats_unwarp, mats_fwd, out=slot["heat"])
+            main.wait_event(slot["done"])  # the exchange / side stream of two batches ago still reads this slot
+        partial_fn = self.partial_sums(imgs_dev, mats_unwarp, mats_fwd, slot["sums"], plan_dev)
+        owned, work, _ = sharded_heatmap_sums(partial_fn, B, N, slot["sums"], group=self.group, plan=plan,
+                                              out=slot["owned"], async_op=True)
         ready = torch.cuda.Event()
         ready.record(main)
-        mine = [b for b in range(B) if owner_of_image(b, world) == rank]
-        slot["mine"] = mine
-        side = self._side  # (on the main stream instead the step is 3 % slower: measured)
+        lo, hi = plan.own
+        side = self._side
         side.wait_event(ready)
+        from . import _lib
+        L = _lib.lib()
         with torch.cuda.stream(side):
-            if mine:
-                sel = heat[mine].contiguous() if len(mine) < B else heat
-                pts, counts, _ = ops.get_pts_from_heatmap_device(sel, self.conf_thresh, self.nms_dist,
+            if work is not None:
+                work.wait()  # the side stream (not the main one) waits for the collective
+            if hi > lo:
+                heat = slot["heat"][:hi - lo]
+                _lib.check(L.spb_ha_finalize_batch(owned.data_ptr(), heat.data_ptr(), hi - lo, H, W, side.cuda_stream),
+                           "ha_finalize")  # export.py:63
+                pts, counts, _ = ops.get_pts_from_heatmap_device(heat, self.conf_thresh, self.nms_dist,
                                                                  self.border_remove, self.top_k, buf["cap"])
-                slot["pts_host"][:len(mine)].copy_(pts, non_blocking=True)
-                slot["cnt_host"][:len(mine)].copy_(counts, non_blocking=True)
+                if self.subpixel_patch:  # model_wrap.py:200-234: all owned images in ONE launch, no host round trip
+                    _lib.check(L.spb_soft_argmax_points_batch(heat.data_ptr(), hi - lo, H, W, pts.data_ptr(),
+                                                              counts.data_ptr(), buf["cap"], self.subpixel_patch,
+                                                              slot["dxdy"].data_ptr(), side.cuda_stream), "soft_argmax")
+                    slot["dxdy_host"][:hi - lo].copy_(slot["dxdy"][:hi - lo], non_blocking=True)
+                slot["pts_host"][:hi - lo].copy_(pts, non_blocking=True)
+                slot["cnt_host"][:hi - lo].copy_(counts, non_blocking=True)
+                slot["pts_dev"], slot["cnt_dev"] = pts, counts  # device-resident consumers (descriptors, matching)
             slot["done"] = torch.cuda.Event()
             slot["done"].record(side)
         return slot
+
+    def heatmaps(self, imgs_dev: torch.Tensor, mats_unwarp: torch.Tensor, mats_fwd: torch.Tensor) -> torch.Tensor:
+        """Aggregated heat-maps [own_hi - own_lo, H, W] of the images this rank owns (all B on a single GPU)."""
+        slot = self.submit_resident(imgs_dev, mats_unwarp, mats_fwd)
+        torch.cuda.current_stream().wait_event(slot["done"])
+        lo, hi = slot["own"]
+        return slot["heat"][:hi - lo]
 
     def submit(self, imgs_host: Sequence[torch.Tensor], mats_unwarp: torch.Tensor, mats_fwd: torch.Tensor):
         """Host images in (pinned for true async copies): H2D + submit_resident.  Returns a ticket for collect().
@@ -160,13 +188,17 @@ class HAExporter:
             return ticket
 
     def collect(self, ticket) -> List[Optional[np.ndarray]]:
-        """Wait for a ticket; float64 [K,3] (x, y, conf) per image this rank owns (b % world == rank), else None."""
+        """Wait for a ticket; float64 [K,3] (x, y, conf) per image this rank owns (``sharding.owned_images``), None
+        for the images other ranks finalise."""
         ticket["done"].synchronize()
-        B = ticket["heat"].shape[0]
-        out: List[Optional[np.ndarray]] = [None] * B
-        for j, b in enumerate(ticket["mine"]):
+        lo, hi = ticket["own"]
+        out: List[Optional[np.ndarray]] = [None] * ticket["B"]
+        for j in range(hi - lo):
             k = int(ticket["cnt_host"][j])
-            out[b] = ticket["pts_host"][j, :k].numpy().astype(np.float64)
+            pts = ticket["pts_host"][j, :k].numpy().astype(np.float64)
+            if self.subpixel_patch:  # model_wrap.py:229-231: refined = point + soft-argmax offset - patch // 2
+                pts[:, :2] += ticket["dxdy_host"][j, :k].numpy().astype(np.float64) - self.subpixel_patch // 2
+            out[lo + j] = pts
         return out
 
     def export_batch(self, imgs_host: Sequence[torch.Tensor], mats_unwarp: torch.Tensor, mats_fwd: torch.Tensor):
@@ -178,8 +210,11 @@ class HAExporter:
         return self.export_batch([img_host], mats_unwarp, mats_fwd)[0]
 
     def last_heat(self, B, H, W) -> torch.Tensor:
+        """Heat-maps [owned,H,W] of the most recent batch of this shape (valid after its collect())."""
         buf = self._buffers(B, H, W)
-        return buf["slots"][(buf["k"] - 1) & 1]["heat"]
+        slot = buf["slots"][(buf["k"] - 1) & 1]
+        lo, hi = slot["own"]
+        return slot["heat"][:hi - lo]
 
 
 def export_detector_homoAdapt_b200(config, output_dir, args=None, loader=None, net: SuperPointNet_b200 = None):
@@ -204,10 +239,17 @@ def export_detector_homoAdapt_b200(config, output_dir, args=None, loader=None, n
         ckpt = torch.load(path, map_location=lambda storage, loc: storage)
         net = SuperPointNet_b200()
         net.load_state_dict(ckpt["model_state_dict"] if path[-4:] == ".tar" else ckpt)
-    from .subpixel import soft_argmax_points
-    exporter = HAExporter(net, conf_thresh, nms_dist, top_k)
+    sub = config["model"].get("subpixel", {}) or {}
+    subpixel = bool(sub.get("enable", False))
+    # export.py:314-319 refines with patch_size = config['model']['subpixel']['patch_size'] (5 in the shipped YAMLs)
+    exporter = HAExporter(net, conf_thresh, nms_dist, top_k, subpixel_patch=int(sub.get("patch_size", 5)) if subpixel else 0)
     rank, world = world_info()
-    subpixel = bool(config["model"].get("subpixel", {}).get("enable", False))
+    # datasets/Coco.py:281-283 erodes the valid masks of the views with this margin (0 in every shipped export YAML);
+    # the fused path keeps the masks as bits inside one kernel chain and has no erosion stage -> refuse, do not ignore
+    margin = (((config["data"].get("augmentation") or {}).get("homographic") or {}).get("valid_border_margin", 0)) or 0
+    if margin:
+        raise NotImplementedError("data.augmentation.homographic.valid_border_margin != 0 is not supported by the fused "
+                                  "export path (use ops.compute_valid_mask(erosion_radius=...) + ops.combine_heatmap)")
     batch_images = max(1, int(config["model"].get("b200_batch_images", 8)))  # images per GPU step (ours, optional)
     seed0 = int(config.get("seed", 0)) * 1000003  # every rank draws the same matrices for image k (shards must agree)
     from concurrent.futures import ThreadPoolExecutor
@@ -223,8 +265,6 @@ def export_detector_homoAdapt_b200(config, output_dir, args=None, loader=None, n
             if pts is None:  # another rank owns this image
                 continue
             target, scene = metas[b]
-            if subpixel:
-                pts = soft_argmax_points(ticket["heat"][b], pts.T, 5).T
             if scene is not None:
                 os.makedirs(os.path.join(save_output, scene), exist_ok=True)
             writes.append(writers.submit(np.savez_compressed, target, pts=pts))
@@ -237,8 +277,12 @@ def export_detector_homoAdapt_b200(config, output_dir, args=None, loader=None, n
         if not batch:
             return
         imgs = [m[0] for m in batch]
-        if all(m[1] is not None for m in batch):
+        have = [m[1] is not None for m in batch]
+        if all(have):
             mu, mf = torch.stack([m[1] for m in batch]), torch.stack([m[2] for m in batch])
+        elif any(have):
+            raise ValueError("a batch mixes samples with and without 'homographies': refusing to discard the provided "
+                             "matrices (flush the loader per kind, or provide them for every sample)")
         else:  # drawn on the GPU, one launch per batch (the host sampler costs ~2 s per 100, like the reference's)
             mu, mf = sample_ha_homographies_device(num, len(batch), seed=seed0 + seen,
                                                    params=ha["homographies"]["params"])
@@ -257,7 +301,7 @@ def export_detector_homoAdapt_b200(config, output_dir, args=None, loader=None, n
         img = torch.as_tensor(np.asarray(img), dtype=torch.float32).squeeze()
         if img.dim() != 2:
             raise ValueError(f"expected one gray image per sample, got {tuple(img.shape)}")
-        if batch and batch[0][0].shape != img.shape:
+        if batch and (batch[0][0].shape != img.shape or (batch[0][1] is not None) != ("homographies" in sample)):
             flush()
         mu = mf = None
         if "homographies" in sample:

@@ -178,14 +178,7 @@ def _extract_batch(self, inp, top_k=0):
         _lib.check(_lib.lib().spb_flatten_detection(semi.data_ptr(), 65, heat.data_ptr(), B, H // 8, W // 8,
                                                     torch.cuda.current_stream().cuda_stream), "flatten_detection")
     pts, counts, _ = ops.get_pts_from_heatmap_device(heat, self.conf_thresh, self.nms_dist, self.border_remove, top_k)
-    out = torch.zeros((B, pts.shape[1], desc.shape[-1]), device=dev, dtype=torch.float32)
-    L = _lib.lib()
-    with torch.cuda.device(dev):
-        st = torch.cuda.current_stream().cuda_stream
-        for b in range(B):
-            _lib.check(L.spb_sample_desc_from_points(desc[b].data_ptr(), 1, pts[b].data_ptr(), counts[b:b + 1].data_ptr(),
-                                                     pts.shape[1], H // self.cell, W // self.cell, desc.shape[-1],
-                                                     self.cell, out[b].data_ptr(), st), "sample_desc_from_points")
+    out = ops.sample_desc_batch_device(desc, pts, counts, cell=self.cell)  # one launch for the batch
     self.heatmap = heat[:, None]
     return pts, counts, out
 

@@ -37,6 +37,14 @@ _GAUSS2 = {
 }
 
 
+def _norm_device(device=None) -> torch.device:
+    """Explicit CUDA device index (``cuda`` != ``cuda:0`` for torch.device comparisons)."""
+    d = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    if d.type != "cuda":
+        raise RuntimeError("SuperPointNet_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    return d if d.index is not None else torch.device("cuda", torch.cuda.current_device())
+
+
 def fold_state_dict(state_dict, eps: float = 1e-5):
     """Any reference layout -> 12 (weight OIHW fp32, bias fp32) numpy pairs with eval-mode BN folded in."""
     sd = {(k[7:] if k.startswith("module.") else k): v for k, v in state_dict.items()}
@@ -71,6 +79,8 @@ class SuperPointNet_b200(nn.Module):
         self._handle_dev = None
         self._ws = None
         self._impl = impl
+        self._ha_overlap = False  # C-handle settings live here and are re-applied whenever the handle is rebuilt
+        self._profile = False
         self.output = None
         # default initialisation = torch's Conv2d default, gauss2 naming (reference default model)
         for name, (cin, cout, ks) in zip(LAYER_NAMES, LAYER_SHAPES):
@@ -112,7 +122,8 @@ class SuperPointNet_b200(nn.Module):
         if self._handle is not None:
             _lib.check(_lib.lib().spb_net_set_impl(self._handle, {"tcgen05": 0, "simt": 1}[impl]), "net_set_impl")
 
-    def handle(self, dev: torch.device):
+    def handle(self, dev):
+        dev = _norm_device(dev)
         if self._handle is not None and self._handle_dev != dev:
             self._release()
         if self._handle is None:
@@ -125,9 +136,19 @@ class SuperPointNet_b200(nn.Module):
                 _lib.check(L.spb_net_create(C.byref(h), arr, brr), "net_create")
             self._handle, self._handle_dev = h, dev
             self.set_impl(self._impl)
+            _lib.check(L.spb_net_set_ha_overlap(h, int(self._ha_overlap)), "set_ha_overlap")
+            _lib.check(L.spb_net_profile(h, int(self._profile)), "net_profile")
         return self._handle
 
+    def set_profile(self, on: bool, device=None) -> None:
+        """Per-stage CUDA-event timing inside the library (bench.py's roofline); read with spb_net_profile_read."""
+        self._profile = bool(on)
+        if self._handle is not None or device is not None:
+            _lib.check(_lib.lib().spb_net_profile(self.handle(device if device is not None else self._handle_dev),
+                                                  int(self._profile)), "net_profile")
+
     def _workspace(self, nbytes: int, dev):
+        dev = _norm_device(dev)
         if self._ws is None or self._ws.numel() < nbytes or self._ws.device != dev:
             self._ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
         return self._ws
@@ -183,20 +204,27 @@ class SuperPointNet_b200(nn.Module):
                                          None if sums is None else sums.reshape(1, 2, H, W), accumulate, chunk)
         return out[0]
 
+    def ha_pass_views(self, H: int, W: int, device=None) -> int:
+        """Views the library puts into one pass at this resolution (bounded by bytes; spb_ha_pass_views)."""
+        dev = _norm_device(device)
+        return int(_lib.lib().spb_ha_pass_views(self.handle(dev), int(H), int(W)))
+
     def ha_heatmap_sums_ragged(self, imgs, mats_unwarp, mats_fwd, view_image, view_offsets, max_views, sums=None,
-                               accumulate=False):
-        """Balanced homography sharding: imgs [B,H,W]; V views as a flat list -- mats [V,3,3], ``view_image`` int32 [V]
-        (image of every view, grouped by image), ``view_offsets`` int32 [B+1], ``max_views`` = the largest per-image
-        count -> sums [B,2,H,W].  One pass over all V views."""
+                               accumulate=False, view_mat=None):
+        """Homography sharding, ONE pass: imgs [B,H,W]; V views as a flat list -- ``view_image`` int32 [V] (image of
+        every view, grouped by image), ``view_offsets`` int32 [B+1], ``max_views`` = the largest per-image count;
+        ``view_mat`` int32 [V] indexes the matrix arrays (any [M,3,3] / [B,N,3,3], flattened), or None with mats
+        [V,3,3] listed in view order -> sums [B,2,H,W]."""
         dev = imgs.device
         B, H, W = imgs.shape
         mu = mats_unwarp.to(dev, torch.float32).contiguous()
         mf = mats_fwd.to(dev, torch.float32).contiguous()
-        V = mu.shape[0]
         vi = view_image.to(dev, torch.int32).contiguous()
         vo = view_offsets.to(dev, torch.int32).contiguous()
-        if vi.numel() != V or vo.numel() != B + 1:
-            raise ValueError("view_image must be [V] and view_offsets [B+1]")
+        V = vi.numel()
+        vm = None if view_mat is None else view_mat.to(dev, torch.int32).contiguous()
+        if vo.numel() != B + 1 or (vm is None and mu.reshape(-1, 3, 3).shape[0] != V) or (vm is not None and vm.numel() != V):
+            raise ValueError("view_image / view_mat must be [V] and view_offsets [B+1]")
         h = self.handle(dev)
         L = _lib.lib()
         nbytes = L.spb_ha_workspace_bytes_ragged(B, V, int(max_views), H, W)
@@ -207,15 +235,18 @@ class SuperPointNet_b200(nn.Module):
         assert sums.is_contiguous()
         with torch.cuda.device(dev):
             _lib.check(L.spb_ha_heatmap_sums_ragged(h, imgs.contiguous().data_ptr(), mu.data_ptr(), mf.data_ptr(),
-                                                    vi.data_ptr(), vo.data_ptr(), B, V, int(max_views), H, W,
-                                                    sums.data_ptr(), int(bool(accumulate)), ws.data_ptr(), ws.numel(),
+                                                    vi.data_ptr(), None if vm is None else vm.data_ptr(), vo.data_ptr(),
+                                                    B, V, int(max_views), H, W, sums.data_ptr(),
+                                                    int(bool(accumulate)), ws.data_ptr(), ws.numel(),
                                                     torch.cuda.current_stream().cuda_stream), "ha_heatmap_sums_ragged")
         return sums
 
     def set_ha_overlap(self, on: bool, device=None) -> None:
         """Overlap the image warp / aggregate of neighbouring passes with the detector net (default off)."""
-        dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
-        _lib.check(_lib.lib().spb_net_set_ha_overlap(self.handle(dev), int(bool(on))), "set_ha_overlap")
+        self._ha_overlap = bool(on)
+        if self._handle is not None or device is not None:
+            dev = _norm_device(device if device is not None else self._handle_dev)
+            _lib.check(_lib.lib().spb_net_set_ha_overlap(self.handle(dev), int(self._ha_overlap)), "set_ha_overlap")
 
     def ha_heatmap_sums_batch(self, imgs, mats_unwarp, mats_fwd, sums=None, accumulate=False, chunk: int = 0):
         """imgs [B,H,W] cuda fp32; mats [N,3,3] shared by the batch or [B,N,3,3] -> sums [B,2,H,W].

@@ -16,7 +16,8 @@ from . import _lib
 
 __all__ = ["inv_warp_image_batch", "compute_valid_mask", "flattenDetection", "combine_heatmap",
            "getPtsFromHeatmap", "get_pts_from_heatmap_device", "sample_desc_from_points",
-           "sample_desc_device", "ha_aggregate", "ha_finalize"]
+           "sample_desc_device", "sample_desc_batch_device", "nn_match_pairs_device", "ha_aggregate", "ha_finalize",
+           "ha_warp_views"]
 
 
 def _dev(device=None) -> torch.device:
@@ -87,6 +88,33 @@ def compute_valid_mask(image_shape, inv_homography, device=None, erosion_radius=
             host[i] = cv2.erode(host[i], k, iterations=1)
         out = torch.from_numpy(host).to(dev)
     return _back(out, device)
+
+
+def ha_warp_views(imgs, mats_fwd, view_image=None):
+    """The image side of the HA branch (datasets/Coco.py:279-282) with the kernels of the fused pass: imgs [nb,H,W]
+    (or [H,W]); mats_fwd [V,3,3]; view_image int [V] (default: all views belong to image 0, or V/nb views per image
+    in order).  Returns (views [V,H,W] fp32, bits [V,H,W/8] uint8): the views within ~1e-3 of
+    ``inv_warp_image_batch``, the packed valid masks EXACTLY those of ``compute_valid_mask``."""
+    dev = _dev(imgs.device if torch.is_tensor(imgs) and imgs.is_cuda else None)
+    x = _cu(imgs, dev)
+    if x.dim() == 2:
+        x = x[None]
+    nb, H, W = x.shape
+    m = _cu(mats_fwd, dev).reshape(-1, 3, 3)
+    V = m.shape[0]
+    if view_image is None:
+        if V % nb:
+            raise ValueError(f"{V} views do not divide over {nb} images: pass view_image")
+        view_image = torch.arange(V, device=dev, dtype=torch.int32) // (V // nb)
+    vi = torch.as_tensor(view_image).to(dev, torch.int32).contiguous()
+    views = torch.empty((V, H, W), device=dev, dtype=torch.float32)
+    bits = torch.empty((V, H, W // 8), device=dev, dtype=torch.uint8)
+    L = _lib.lib()
+    ws = torch.empty(int(L.spb_ha_warp_views_workspace_bytes(nb, V, H, W)), device=dev, dtype=torch.uint8)
+    with torch.cuda.device(dev):
+        _lib.check(L.spb_ha_warp_views(x.data_ptr(), m.data_ptr(), vi.data_ptr(), None, nb, V, H, W, views.data_ptr(),
+                                       bits.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), "ha_warp_views")
+    return views, bits
 
 
 def flattenDetection(semi, tensor=False):
@@ -198,6 +226,46 @@ def sample_desc_device(coarse, pts, count=None, nhwc=False, cell=8):
             coarse.data_ptr(), int(nhwc), pts.data_ptr(), count.data_ptr() if count is not None else None, K, Hc, Wc,
             D, cell, out.data_ptr(), _stream()), "sample_desc_from_points")
     return out
+
+
+def sample_desc_batch_device(coarse_nhwc, pts, counts, cell=8, normalize=True):
+    """ONE launch for a batch: coarse [B,Hc,Wc,D] cuda fp32 (the network's NHWC output), pts [B,K,3], counts [B] int32
+    -> [B,K,D] unit-norm descriptors, the rows behind counts[b] zero filled.  No host synchronisation."""
+    coarse = coarse_nhwc.contiguous()
+    B, Hc, Wc, D = coarse.shape
+    K = pts.shape[1]
+    out = torch.empty((B, K, D), device=coarse.device, dtype=torch.float32)
+    if K == 0 or B == 0:
+        return out
+    with torch.cuda.device(coarse.device):
+        _lib.check(_lib.lib().spb_sample_desc_batch(coarse.data_ptr(), pts.contiguous().data_ptr(), counts.data_ptr(), B,
+                                                    K, Hc, Wc, D, cell, int(bool(normalize)), out.data_ptr(), _stream()),
+                   "sample_desc_batch")
+    return out
+
+
+def nn_match_pairs_device(desc1, desc2, nn_thresh):
+    """Two-way matching of P image pairs in one launch (models/model_wrap.py:437-480 per pair): desc1 / desc2 [P,K,D]
+    point-major cuda fp32, zero rows = padding -> (idx1 [P,K] int32, idx2, score [P,K] fp32, count [P] int32) on the
+    device; pair p's matches are the first count[p] entries, ascending idx1."""
+    if nn_thresh < 0.0:
+        raise ValueError("'nn_thresh' should be non-negative")
+    d1, d2 = desc1.contiguous(), desc2.contiguous()
+    P, K, D = d1.shape
+    if tuple(d2.shape) != (P, K, D):
+        raise ValueError("nn_match_pairs_device: both descriptor sets must be [P,K,D]")
+    dev = d1.device
+    idx1 = torch.empty((P, K), dtype=torch.int32, device=dev)
+    idx2 = torch.empty((P, K), dtype=torch.int32, device=dev)
+    score = torch.empty((P, K), dtype=torch.float32, device=dev)
+    count = torch.empty((P,), dtype=torch.int32, device=dev)
+    L = _lib.lib()
+    ws = torch.empty(int(L.spb_nn_match_pairs_workspace_bytes(P, K)), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(L.spb_nn_match_pairs(d1.data_ptr(), d2.data_ptr(), P, K, D, float(nn_thresh), idx1.data_ptr(),
+                                        idx2.data_ptr(), score.data_ptr(), count.data_ptr(), ws.data_ptr(), ws.numel(),
+                                        _stream()), "nn_match_pairs")
+    return idx1, idx2, score, count
 
 
 def sample_desc_from_points(coarse_desc, pts, cell=8):

@@ -16,7 +16,8 @@ def soft_argmax_points(heat, pts, patch_size: int = 5) -> np.ndarray:
     if not torch.cuda.is_available():
         raise RuntimeError("soft_argmax_points needs a CUDA device; there is no CPU fallback")
     h = torch.as_tensor(heat) if not torch.is_tensor(heat) else heat
-    h = h.to("cuda", torch.float32).squeeze().contiguous()
+    dev = h.device if h.is_cuda else torch.device("cuda", torch.cuda.current_device())  # stay on the heat-map's GPU
+    h = h.to(dev, torch.float32).squeeze().contiguous()
     H, W = h.shape
     K = pts.shape[1]
     out = np.array(pts, dtype=np.float64, copy=True)

@@ -116,9 +116,16 @@ def test_cabi_argument_errors_without_a_gpu():
     assert L.spb_roi_soft_argmax(None, 1, 8, 8, None, 3, p(buf), None, None) < 0
     assert L.spb_sample_desc_from_points_ex(p(buf), 1, p(buf), 1, None, 4, 4, 4, 8, 8, 0, p(buf), None) < 0  # stride < 2
     # ragged HA entry: a NULL network handle
-    assert L.spb_ha_heatmap_sums_ragged(None, p(buf), p(buf), p(buf), p(ibuf), p(ibuf), 1, 1, 1, 8, 8, p(buf), 0, p(buf),
-                                        64, None) < 0
+    assert L.spb_ha_heatmap_sums_ragged(None, p(buf), p(buf), p(buf), p(ibuf), p(ibuf), p(ibuf), 1, 1, 1, 8, 8, p(buf), 0,
+                                        p(buf), 64, None) < 0
     assert L.spb_ha_workspace_bytes_ragged(0, 1, 1, 8, 8) == 0
+    # pass size: bounded by bytes (800 views of 240x320), at least one view
+    assert L.spb_ha_pass_views(None, 240, 320) == 800 and L.spb_ha_pass_views(None, 480, 640) == 200
+    assert L.spb_ha_pass_views(None, 384, 1248) == 128 and L.spb_ha_pass_views(None, 4096, 4096) == 3
+    # fused-pass warp on its own: W must be a multiple of 8, workspace checked
+    assert L.spb_ha_warp_views(p(buf), p(buf), p(ibuf), None, 1, 1, 8, 12, p(buf), p(buf), p(buf), 1 << 20, None) < 0
+    assert L.spb_ha_warp_views(p(buf), p(buf), p(ibuf), None, 1, 1, 8, 8, p(buf), p(buf), p(buf), 16, None) == -3
+    assert L.spb_ha_warp_views_workspace_bytes(1, 0, 8, 8) == 0
     # pass-overlap switch and pass size: a NULL network handle
     assert L.spb_net_set_ha_overlap(None, 1) < 0
     assert L.spb_net_set_ha_chunk(None, 100) < 0

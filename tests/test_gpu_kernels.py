@@ -124,6 +124,73 @@ def test_fused_aggregate_extreme_scale_fallback(spb):
     assert np.abs(heat - ref).max() < 2e-6
 
 
+# ------------------------------------------------------------------- fused-pass warp (folded coordinates)
+def _packed_mask(spb, H, W, inv):
+    m = spb.compute_valid_mask((H, W), torch.from_numpy(inv).cuda()).cpu().numpy().astype(np.uint8)
+    return np.packbits(m, axis=-1, bitorder="little")
+
+
+@pytest.mark.parametrize("H,W,N,seed", [(240, 320, 800, 1), (480, 640, 96, 2), (384, 1248, 64, 3), (48, 64, 40, 4),
+                                        (40, 24, 9, 5), (64, 96, 33, 6)])
+def test_fast_warp_views_mask_bits_exact_and_values_close(spb, H, W, N, seed):
+    """The warp of the fused HA pass (ha_fast.cu: folded homography, reciprocal, magic-number floor) against the
+    bit-exact operators: the packed valid masks must be IDENTICAL to compute_valid_mask (ambiguous pixels are
+    re-evaluated with the exact expression), the views agree with inv_warp_image_batch to ~1e-3."""
+    from pytorch_superpoint_b200 import ops
+    rng = np.random.RandomState(seed)
+    img = rng.rand(H, W).astype(np.float32)
+    _, inv = _mats(N, seed)
+    views, bits = ops.ha_warp_views(torch.from_numpy(img).cuda(), torch.from_numpy(inv).cuda())
+    assert np.array_equal(bits.cpu().numpy(), _packed_mask(spb, H, W, inv))
+    exact = spb.inv_warp_image_batch(torch.from_numpy(img).cuda(), torch.from_numpy(inv).cuda())[:, 0]
+    assert (views - exact).abs().max().item() < 2e-3  # white-noise image: gradients of ~1 per pixel
+
+
+def test_fast_warp_views_reference_masks_and_batched_images(spb, golden):
+    """Mask bits against the masks of the UNMODIFIED reference at the bench shape (100 views of 240x320), and a
+    batch of images with a per-view image index."""
+    from pytorch_superpoint_b200 import ops
+    g = golden("mask_240x320_n100")
+    ref = np.unpackbits(g["mask_bits"])[: np.prod(g["shape"])].reshape(g["shape"]).astype(np.uint8)
+    _, bits = ops.ha_warp_views(torch.zeros(240, 320).cuda(), torch.from_numpy(g["inv"]).cuda())
+    got = np.unpackbits(bits.cpu().numpy(), axis=-1, bitorder="little")
+    assert np.array_equal(got, O.compute_valid_mask((240, 320), g["inv"]).astype(np.uint8))  # exact vs the oracle
+    assert int((got != ref).sum()) <= 8                                                      # and the reference
+    rng = np.random.RandomState(7)
+    imgs = rng.rand(3, 64, 96).astype(np.float32)
+    _, inv = _mats(7, 9)
+    vi = np.array([0, 0, 1, 2, 2, 2, 1], np.int32)
+    views, bits = ops.ha_warp_views(torch.from_numpy(imgs).cuda(), torch.from_numpy(inv).cuda(), view_image=vi)
+    for v in range(7):
+        exact = O.inv_warp_image_batch(imgs[vi[v]][None], inv[v:v + 1], "bilinear")[0]
+        assert np.abs(views[v].cpu().numpy() - exact).max() < 2e-3
+    assert np.array_equal(bits.cpu().numpy(), _packed_mask(spb, 64, 96, inv))
+
+
+def test_fast_warp_views_extreme_homographies(spb):
+    """Strong perspective (denominator close to / through zero inside the frame), huge scales, a singular and a NaN
+    matrix: the mask bits stay exactly those of the reference expression (these views fall back to it) and nothing
+    reads out of bounds."""
+    from pytorch_superpoint_b200 import ops
+    H, W = 64, 96
+    rng = np.random.RandomState(3)
+    mats = [np.eye(3), np.diag([8.0, 8.0, 1.0]), np.diag([0.05, 0.05, 1.0]),
+            np.array([[1, 0, 0], [0, 1, 0], [0.9, 0.0, 1.0]]),      # Z = 1 + 0.9 u: down to 0.1
+            np.array([[1, 0, 0], [0, 1, 0], [1.2, 0.3, 1.0]]),      # Z changes sign inside the frame
+            np.array([[1, 0.2, 0.5], [0.1, 1, -0.7], [0.0, 0.0, 1e-3]]),
+            np.zeros((3, 3)), np.full((3, 3), np.nan),
+            np.array([[1, 0, 1e-7], [0, 1, 0], [0, 0, 1]]),         # borders within rounding of the decision boundary
+            np.array([[1.0000001, 0, 0], [0, 0.9999999, 0], [0, 0, 1]])]
+    for _ in range(30):
+        m = np.eye(3) + rng.randn(3, 3) * np.array([[0.3, 0.3, 0.5], [0.3, 0.3, 0.5], [0.6, 0.6, 0.2]])
+        mats.append(m)
+    inv = np.stack(mats).astype(np.float32)
+    img = rng.rand(H, W).astype(np.float32)
+    views, bits = ops.ha_warp_views(torch.from_numpy(img).cuda(), torch.from_numpy(inv).cuda())
+    assert torch.isfinite(views).all()
+    assert np.array_equal(bits.cpu().numpy(), _packed_mask(spb, H, W, inv))
+
+
 # ---------------------------------------------------------------------------------------------- NMS
 CASES = ["smooth_96x128", "flat_random_240x320", "sparse_64x80", "ties_72x88", "empty_40x48", "single_40x48",
          "border_40x48"]
