@@ -287,9 +287,14 @@ def run_b200(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # NCCL_DEBUG is left as the caller set it (the communicator lines "... rank r nranks N ..." are the evidence of
+    # the rank count).  NCCL writes them to file descriptor 1, also at process exit, behind anything this script
+    # prints: to keep stdout to the ONE JSON line, fd 1 is pointed at stderr for the life of the process and the
+    # JSON line goes to a duplicate of the original stdout.
+    json_fd = os.dup(1)
+    sys.stdout.flush()
+    os.dup2(2, 1)
     if world > 1:
-        # (NCCL_DEBUG is left as the caller set it: the communicator lines are the driver's evidence of the rank count;
-        # the JSON line is printed last, after the process group is gone)
         dist.init_process_group("nccl", device_id=dev)
     L = _lib.lib()
     wl = WORKLOADS[args.workload]
@@ -558,8 +563,7 @@ def run_b200(args):
         except Exception:
             pass
     if rank == 0:
-        sys.stderr.flush()
-        print("\n" + json.dumps(line), flush=True)  # own line, after NCCL's teardown messages
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     return 0
 
 

@@ -10,8 +10,9 @@
 // Both gathers were issue bound in round 1 (two IEEE divisions, per-tap validity tests, cell-major index
 // arithmetic: ~150 and ~250 instructions per pixel, 8 % of the HBM roofline).  Here every view's homography is
 // folded once (common.cuh: FoldMat), the frames carry a border so that clamped coordinates replace the per-tap
-// tests, floor() is one magic-number addition and the planes are row-major: ~45 / ~55 instructions per pixel.
-// A lane works on pixels 32 apart, so that every load / store instruction of a warp touches 32 neighbouring pixels.
+// tests, floor() is one magic-number addition and the planes are row-major: ~50 / ~65 instructions per pixel.
+// A warp works on an 8 x 4 pixel block: with rotations of up to +-90 degrees that keeps the number of cache lines a
+// gather instruction touches at 4..9 (a 32 x 1 row: ~20), the quantity the L1 tag stage bounds these kernels by.
 // The valid-mask bit is still EXACT: decided from the folded coordinate when that is further than an epsilon from
 // the decision boundary, re-evaluated with the reference's rounded fp32 expression (common.cuh: nearest_valid)
 // otherwise (a few pixels per view).
@@ -116,10 +117,15 @@ struct WarpArgs {
   Lin lx, ly;
 };
 
-constexpr int kWarpRows = 16;  // rows per CTA (2 per warp)
+// A warp covers 8 x 4 output pixels (not 32 x 1): the sampler draws rotations up to +-90 degrees, under which a
+// 32-pixel row of the output maps to a source segment crossing ~20 rows = ~20 cache lines per load instruction, and
+// the round-2 ncu capture showed the first version of this kernel bound by the L1 tag stage (l1tex 70-85 %), not by
+// issue slots.  An 8 x 4 block touches 4..9 source rows at every angle.
+constexpr int kWarpRows = 32;  // rows per CTA: 8 warps x 4 rows, the CTA walks along x
 
 __global__ void __launch_bounds__(256) warp_views_kernel(WarpArgs a) {
   const int view = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lx = lane & 7, ly = lane >> 3;
   const FoldMat f = a.fold[view];
   const int Wp = a.W + 2 * kHaPad, Hp = a.H + 2 * kHaPad;
   const float* src = a.src_pad + (long long)a.vm.img(view) * Hp * Wp;
@@ -135,42 +141,46 @@ __global__ void __launch_bounds__(256) warp_views_kernel(WarpArgs a) {
   const float oly = kHaPad - eps, ohy = (float)a.H + kHaPad + eps;
   const unsigned kmagic = 0x4B000000u * (unsigned)(Wp + 1);  // (mod 2^32: the offsets below wrap consistently)
   const int Wb = a.W >> 3;
+  const int y = blockIdx.x * kWarpRows + warp * 4 + ly;
+  const bool row_ok = y < a.H;
+  const int yc = row_ok ? y : a.H - 1;
+  const float yf = (float)yc;
+  const float nx0 = fmaf(f.ax1, yf, f.ax2), ny0 = fmaf(f.ay1, yf, f.ay2), nz0 = fmaf(f.z1, yf, f.z2);
+  float* orow = a.out + ((long long)view * a.H + yc) * a.W;
+  uint8_t* brow = a.bits + ((long long)view * a.H + yc) * Wb;
+  if (blockIdx.x * kWarpRows + warp * 4 >= a.H) return;  // (warp-uniform: no row of this warp exists)
 #pragma unroll 1
-  for (int ry = 0; ry < kWarpRows / 8; ++ry) {
-    const int y = blockIdx.x * kWarpRows + ry * 8 + warp;
-    if (y >= a.H) break;  // (warp-uniform)
-    const float yf = (float)y;
-    const float nx0 = fmaf(f.ax1, yf, f.ax2), ny0 = fmaf(f.ay1, yf, f.ay2), nz0 = fmaf(f.z1, yf, f.z2);
-    float* orow = a.out + ((long long)view * a.H + y) * a.W;
-    uint8_t* brow = a.bits + ((long long)view * a.H + y) * Wb;
-#pragma unroll 1
-    for (int xc = 0; xc < a.W; xc += 64) {
-      float val[2];
-      unsigned word[2];
+  for (int xc = 0; xc < a.W; xc += 16) {
+    float val[2];
+    unsigned word[2];
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int x = xc + 32 * j + lane;
-        const float xf = (float)x;
-        const float r = rcp_approx(fmaf(f.z0, xf, nz0));
-        const float sx = fmaf(f.ax0, xf, nx0) * r, sy = fmaf(f.ay0, xf, ny0) * r;
-        const Tap1 tx = tap_axis(sx, clx, chx), ty = tap_axis(sy, cly, chy);
-        const unsigned off = ty.bits * (unsigned)Wp + tx.bits - kmagic;  // south-east tap: row, column >= 2
-        const float *p = src + off, *q0 = src + (off - (unsigned)Wp);
-        const float top = fmaf(__ldg(q0), tx.w1, __ldg(q0 - 1) * tx.w0);
-        const float bot = fmaf(__ldg(p), tx.w1, __ldg(p - 1) * tx.w0);
-        val[j] = fmaf(bot, ty.w1, top * ty.w0);
-        bool in = sx >= ilx && sx <= ihx && sy >= ily && sy <= ihy;
-        const bool maybe = sx >= olx && sx <= ohx && sy >= oly && sy <= ohy;  // NaN -> false -> invalid (as exact)
-        if (__any_sync(0xffffffffu, maybe && !in)) {
-          if (maybe && !in && x < a.W)
-            in = nearest_valid(load_mat(a.mats_fwd + 9LL * a.vm.mat(view)), a.lx.at(x), a.ly.at(y), a.W, a.H);
-        }
-        word[j] = __ballot_sync(0xffffffffu, in && x < a.W);
+    for (int j = 0; j < 2; ++j) {
+      const int x = xc + 8 * j + lx;  // (W % 8 == 0: a column block of 8 is inside the image or entirely outside)
+      const float xf = (float)x;
+      const float r = rcp_approx(fmaf(f.z0, xf, nz0));
+      const float sx = fmaf(f.ax0, xf, nx0) * r, sy = fmaf(f.ay0, xf, ny0) * r;
+      const Tap1 tx = tap_axis(sx, clx, chx), ty = tap_axis(sy, cly, chy);
+      const unsigned off = ty.bits * (unsigned)Wp + tx.bits - kmagic;  // south-east tap: row, column >= 2
+      const float *p = src + off, *q0 = src + (off - (unsigned)Wp);
+      const float top = fmaf(__ldg(q0), tx.w1, __ldg(q0 - 1) * tx.w0);
+      const float bot = fmaf(__ldg(p), tx.w1, __ldg(p - 1) * tx.w0);
+      val[j] = fmaf(bot, ty.w1, top * ty.w0);
+      bool in = sx >= ilx && sx <= ihx && sy >= ily && sy <= ihy;
+      const bool maybe = sx >= olx && sx <= ohx && sy >= oly && sy <= ohy;  // NaN -> false -> invalid (as exact)
+      const bool live = row_ok && x < a.W;
+      if (__any_sync(0xffffffffu, maybe && !in && live)) {
+        if (maybe && !in && live)
+          in = nearest_valid(load_mat(a.mats_fwd + 9LL * a.vm.mat(view)), a.lx.at(x), a.ly.at(y), a.W, a.H);
       }
-      if (xc + lane < a.W) orow[xc + lane] = val[0];
-      if (xc + 32 + lane < a.W) orow[xc + 32 + lane] = val[1];
-      // lanes 0..7 write the 8 mask bytes of this 64-pixel chunk
-      if (lane < 8 && xc + 8 * lane < a.W) brow[(xc >> 3) + lane] = (uint8_t)(word[lane >> 2] >> ((lane & 3) * 8));
+      word[j] = __ballot_sync(0xffffffffu, in && live);
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int x = xc + 8 * j + lx;
+      if (row_ok && x < a.W) {
+        orow[x] = val[j];
+        if (lx == 0) brow[x >> 3] = (uint8_t)(word[j] >> (ly * 8));  // byte ly of the ballot = 8 pixels of row ly
+      }
     }
   }
 }
@@ -213,8 +223,15 @@ struct AggArgs {
   int N, H, W, G;
 };
 
+constexpr int kAggFoldStage = 128;  // folded matrices staged per round in shared memory
+
+// CTA tile 32 x 8 output pixels, every warp an 8 x 4 block (see warp_views_kernel: the gather is bound by the number
+// of cache lines a load instruction touches, and un-warps rotate by up to +-90 degrees).  The folded matrices of the
+// CTA's views are staged in shared memory (three broadcast LDS instead of three L1 look-ups per view and thread).
 __global__ void __launch_bounds__(256) agg_heat_kernel(AggArgs a) {
-  const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  __shared__ float4 s_fold[kAggFoldStage * 3];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int x = blockIdx.x * 32 + (warp & 3) * 8 + (lane & 7), y = blockIdx.y * 8 + (warp >> 2) * 4 + (lane >> 3);
   const int b = blockIdx.z / a.G, g = blockIdx.z % a.G;
   int n_begin, n_end;
   if (a.offs) {
@@ -230,32 +247,41 @@ __global__ void __launch_bounds__(256) agg_heat_kernel(AggArgs a) {
   const unsigned kmagic = 0x4B000000u * (unsigned)(Wh + 1);
   const float xf = (float)x, yf = (float)y;
   float num = 0.f, den = 0.f;
-  // running pointers: the view's plane (minus the magic-number bias of the tap offsets) and its folded matrix
-  const unsigned short* plane = reinterpret_cast<const unsigned short*>(a.heat16) + (long long)n_begin * Hh * Wh;
-  const long long plane_step = (long long)a.G * Hh * Wh;
-  const float4* fp = reinterpret_cast<const float4*>(a.fold + n_begin);
+  const long long plane_sz = (long long)Hh * Wh;
+  const int nviews = n_end > n_begin ? (n_end - n_begin + a.G - 1) / a.G : 0;  // views n_begin + i * G of this CTA
+  for (int i0 = 0; i0 < nviews; i0 += kAggFoldStage) {
+    const int cnt = min(kAggFoldStage, nviews - i0);
+    __syncthreads();
+    for (int e = threadIdx.x; e < cnt * 3; e += 256)
+      s_fold[e] = __ldg(reinterpret_cast<const float4*>(a.fold + n_begin + (long long)(i0 + e / 3) * a.G) + e % 3);
+    __syncthreads();
+    // running pointer: the view's plane (the tap offsets carry the magic-number bias, removed by kmagic)
+    const unsigned short* plane =
+        reinterpret_cast<const unsigned short*>(a.heat16) + (n_begin + (long long)i0 * a.G) * plane_sz;
+    const long long plane_step = (long long)a.G * plane_sz;
 #pragma unroll 2
-  for (int n = n_begin; n < n_end; n += a.G, plane += plane_step, fp += 3 * a.G) {
-    const float4 f0 = __ldg(fp), f1 = __ldg(fp + 1);
-    const float z2 = __ldg(reinterpret_cast<const float*>(fp + 2));
-    const float r = rcp_approx(fmaf(f1.z, xf, fmaf(f1.w, yf, z2)));
-    const float sx = fmaf(f0.x, xf, fmaf(f0.y, yf, f0.z)) * r;
-    const float sy = fmaf(f0.w, xf, fmaf(f1.x, yf, f1.y)) * r;
-    const Tap1 tx = tap_axis(sx, clx, chx), ty = tap_axis(sy, cly, chy);
-    const unsigned off = ty.bits * (unsigned)Wh + tx.bits - kmagic;  // south-east tap: row >= 2, column >= 8
-    const unsigned short *p = plane + off, *q0 = plane + (off - (unsigned)Wh);
-    const float w00 = tx.w0 * ty.w0, w01 = tx.w1 * ty.w0, w10 = tx.w0 * ty.w1, w11 = tx.w1 * ty.w1;
-    auto tap = [&](const unsigned short* q, float w) {
-      const float pv = __half2float(__ushort_as_half(__ldg(q)));
-      if (pv >= 0.f) {
-        num = fmaf(pv, w, num);
-        den += w;
-      }
-    };
-    tap(q0 - 1, w00);
-    tap(q0, w01);
-    tap(p - 1, w10);
-    tap(p, w11);
+    for (int i = 0; i < cnt; ++i, plane += plane_step) {
+      const float4 f0 = s_fold[3 * i], f1 = s_fold[3 * i + 1];
+      const float z2 = s_fold[3 * i + 2].x;
+      const float r = rcp_approx(fmaf(f1.z, xf, fmaf(f1.w, yf, z2)));
+      const float sx = fmaf(f0.x, xf, fmaf(f0.y, yf, f0.z)) * r;
+      const float sy = fmaf(f0.w, xf, fmaf(f1.x, yf, f1.y)) * r;
+      const Tap1 tx = tap_axis(sx, clx, chx), ty = tap_axis(sy, cly, chy);
+      const unsigned off = ty.bits * (unsigned)Wh + tx.bits - kmagic;  // south-east tap: row >= 2, column >= 8
+      const unsigned short *p = plane + off, *q0 = plane + (off - (unsigned)Wh);
+      const float w00 = tx.w0 * ty.w0, w01 = tx.w1 * ty.w0, w10 = tx.w0 * ty.w1, w11 = tx.w1 * ty.w1;
+      auto tap = [&](const unsigned short* q, float w) {
+        const float pv = __half2float(__ushort_as_half(__ldg(q)));
+        if (pv >= 0.f) {
+          num = fmaf(pv, w, num);
+          den += w;
+        }
+      };
+      tap(q0 - 1, w00);
+      tap(q0, w01);
+      tap(p - 1, w10);
+      tap(p, w11);
+    }
   }
   if (x < a.W && y < a.H) {
     float* o = a.part + (long long)blockIdx.z * 2 * a.H * a.W + (long long)y * a.W + x;
