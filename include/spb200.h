@@ -55,6 +55,13 @@ int spb_inv_warp_image_batch(const float* img, long long img_batch_stride, const
  * nearest-mode warp of an all-ones image -> mask[N,H,W] in {0,1} (fp32, like the reference). */
 int spb_compute_valid_mask(const float* mats, float* mask, int N, int H, int W, void* stream);
 
+/* utils/utils.py:699-702: the erosion of those masks (`cv2.erode(mask, getStructuringElement(MORPH_ELLIPSE,
+ * (2r, 2r)), iterations=1)`, datasets/Coco.py:281-283 `valid_border_margin`).  Generic form: the structuring element
+ * is given as one column span [j1, j2) per row (spans: DEVICE int[kh][2]) with its anchor; pixels outside the image
+ * are ignored (cv2's default erosion border).  in and out [N,H,W] fp32, out != in. */
+int spb_erode(const float* in, float* out, int N, int H, int W, const int* spans, int kh, int anchor_y, int anchor_x,
+              void* stream);
+
 /* ---- (3) heat-map ---------------------------------------------------------------------------------
  * utils/utils.py:480-525 `flattenDetection(semi, tensor=True)` + utils/d2s.py:8-25 DepthToSpace(8):
  * softmax over 65 channels, drop the dustbin, pixel-shuffle.  semi is NCHW fp32 [B,65,Hc,Wc]

@@ -7,8 +7,10 @@ library; calling any operator does, and raises otherwise -- there is no CPU fall
 """
 from .homographies import (EXPORT_PARAMS, make_ha_homographies, sample_ha_homographies_device,  # noqa: F401
                            sample_homography)
-from .net import SuperPointNet_b200, fold_state_dict  # noqa: F401
+from .net import SuperPointNet_b200, SuperPointNet_pretrained_b200, fold_state_dict  # noqa: F401
 from .ops import (combine_heatmap, compute_valid_mask, flattenDetection, getPtsFromHeatmap,  # noqa: F401
                   inv_warp_image_batch, nn_match_two_way, sample_desc_from_points)
 
-__version__ = "0.1.0"
+from .tracker import PointTracker_b200  # noqa: F401
+
+__version__ = "0.2.0"

@@ -25,6 +25,7 @@ PROTOTYPES = {
     "spb_launch_count": (C.c_ulonglong, []),
     "spb_inv_warp_image_batch": (_i, [_p, _ll, _p, _p, _i, _i, _i, _i, _p]),
     "spb_compute_valid_mask": (_i, [_p, _p, _i, _i, _i, _p]),
+    "spb_erode": (_i, [_p, _p, _i, _i, _i, _p, _i, _i, _i, _p]),
     "spb_flatten_detection": (_i, [_p, _i, _p, _i, _i, _i, _p]),
     "spb_combine_heatmap": (_i, [_p, _p, _p, _p, _i, _i, _i, _p]),
     "spb_ha_aggregate_workspace_bytes": (_z, [_i, _i, _i]),

@@ -169,8 +169,7 @@ using namespace spb;
 
 extern "C" {
 
-int spb_net_create(spb_net** out, const float* const* weights, const float* const* biases) {
-  SPB_CHECK_ARG(out && weights && biases);
+static int net_fill(Net* net, const float* const* weights, const float* const* biases) {
   int dev = 0;
   cudaDeviceProp prop;
   SPB_CHECK_CUDA(cudaGetDevice(&dev));
@@ -180,8 +179,6 @@ int spb_net_create(spb_net** out, const float* const* weights, const float* cons
               prop.minor);
     return SPB_EARCH;
   }
-  Net* net = static_cast<Net*>(calloc(1, sizeof(Net)));
-  if (!net) return SPB_ENOMEM;
   net->impl = SPB_IMPL_TCGEN05;
   net->ha_overlap = 0;
   for (int li = 0; li < kNumLayers; ++li) {
@@ -245,6 +242,21 @@ int spb_net_create(spb_net** out, const float* const* weights, const float* cons
         if ((rc = conv_s3_prepare(L)) != SPB_OK) return rc;
       }
     }
+  }
+  return SPB_OK;
+}
+
+int spb_net_destroy(spb_net* h);
+
+int spb_net_create(spb_net** out, const float* const* weights, const float* const* biases) {
+  SPB_CHECK_ARG(out && weights && biases);
+  *out = nullptr;
+  Net* net = static_cast<Net*>(calloc(1, sizeof(Net)));
+  if (!net) return SPB_ENOMEM;
+  const int rc = net_fill(net, weights, biases);
+  if (rc != SPB_OK) {  // free what the failed construction had allocated (device buffers, tensor maps)
+    spb_net_destroy(reinterpret_cast<spb_net*>(net));
+    return rc;
   }
   *out = reinterpret_cast<spb_net*>(net);
   return SPB_OK;

@@ -109,6 +109,28 @@ int warp_with_mask_bits(const float* img, const float* mats, float* out, uint8_t
   return SPB_OK;
 }
 
+// Erosion of the valid masks (utils/utils.py:699-702: cv2.erode with an elliptic structuring element, one
+// iteration): out(y, x) = min over the element's pixels of in(y + i - ay, x + j - ax), pixels outside the image
+// ignored (cv2's default border value for erosion is +max).  The element arrives as one column span [j1, j2) per row
+// (the caller restates cv2.getStructuringElement's formula), so any row-convex element works.
+__global__ void __launch_bounds__(256) erode_kernel(const float* __restrict__ in, float* __restrict__ out, int N,
+                                                    int H, int W, const int* __restrict__ spans, int kh, int ay,
+                                                    int ax) {
+  const long long total = (long long)N * H * W;
+  for (long long t = blockIdx.x * 256LL + threadIdx.x; t < total; t += gridDim.x * 256LL) {
+    const int x = (int)(t % W), y = (int)((t / W) % H);
+    const float* img = in + (t / ((long long)W * H)) * H * W;
+    float m = INFINITY;
+    for (int i = 0; i < kh; ++i) {
+      const int yy = y + i - ay;
+      if (yy < 0 || yy >= H) continue;
+      const int j1 = max(__ldg(spans + 2 * i) - ax + x, 0), j2 = min(__ldg(spans + 2 * i + 1) - ax + x, W);
+      for (int xx = j1; xx < j2; ++xx) m = fminf(m, __ldg(img + (long long)yy * W + xx));
+    }
+    out[t] = m;
+  }
+}
+
 template <int MODE>
 static int launch_warp(const float* img, long long stride, const float* mats, float* out, int N, int H, int W,
                        cudaStream_t st) {
@@ -147,6 +169,19 @@ int spb_compute_valid_mask(const float* mats, float* mask, int N, int H, int W, 
   SPB_CHECK_ARG(N >= 0 && H >= 2 && W >= 2);
   if (N == 0) return SPB_OK;
   return launch_warp<2>(mask /*unused*/, 0, mats, mask, N, H, W, as_stream(stream));
+}
+
+int spb_erode(const float* in, float* out, int N, int H, int W, const int* spans, int kh, int anchor_y, int anchor_x,
+              void* stream) {
+  SPB_CHECK_ARG(in && out && spans && in != out);
+  SPB_CHECK_ARG(N >= 0 && H >= 1 && W >= 1 && kh >= 1 && kh <= 256 && anchor_y >= 0 && anchor_y < kh && anchor_x >= 0);
+  if (N == 0) return SPB_OK;
+  const long long total = (long long)N * H * W;
+  int blocks = ceil_div(total, 256);
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  erode_kernel<<<blocks, 256, 0, as_stream(stream)>>>(in, out, N, H, W, spans, kh, anchor_y, anchor_x);
+  SPB_CHECK_LAUNCH();
+  return SPB_OK;
 }
 
 }  // extern "C"

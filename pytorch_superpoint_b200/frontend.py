@@ -186,25 +186,4 @@ def _extract_batch(self, inp, top_k=0):
 SuperPointFrontend_b200.extract_batch = _extract_batch
 
 
-class PointTracker_b200(object):
-    """The matching half of ``models/model_wrap.py:411-583 PointTracker``: ``nn_match_two_way`` on the GPU
-    (same arguments, float64 ``[3,L]`` result, ``mscores`` attribute, ValueError on a negative threshold)."""
-
-    def __init__(self, max_length=2, nn_thresh=0.7):
-        if max_length < 2:
-            raise ValueError("max_length must be greater than or equal to 2.")
-        self.maxl = max_length
-        self.nn_thresh = nn_thresh
-        self.mscores = None
-        self.matches = None
-
-    def nn_match_two_way(self, desc1, desc2, nn_thresh):
-        matches = ops.nn_match_two_way(desc1, desc2, nn_thresh)
-        self.mscores = matches
-        return matches
-
-    def get_matches(self):
-        return self.matches
-
-    def get_mscores(self):
-        return self.mscores
+from .tracker import PointTracker_b200  # noqa: E402,F401  (models/model_wrap.py:411-583; kept importable from here)

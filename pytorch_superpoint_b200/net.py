@@ -274,3 +274,12 @@ class SuperPointNet_b200(nn.Module):
                                                    ws.data_ptr(), ws.numel(),
                                                    torch.cuda.current_stream().cuda_stream), "ha_heatmap_sums_batch")
         return sums
+
+
+class SuperPointNet_pretrained_b200(SuperPointNet_b200):
+    """Drop-in for ``models/SuperPointNet_pretrained.py:10-76`` (MagicLeap ``superpoint_v1.pth``): the same network,
+    ``forward`` returns the TUPLE ``(semi, desc)`` of that class instead of the dict of the other two layouts."""
+
+    def forward(self, x):
+        out = super().forward(x)
+        return out["semi"], out["desc"]

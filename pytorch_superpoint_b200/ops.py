@@ -14,7 +14,7 @@ import torch
 
 from . import _lib
 
-__all__ = ["inv_warp_image_batch", "compute_valid_mask", "flattenDetection", "combine_heatmap",
+__all__ = ["inv_warp_image_batch", "compute_valid_mask", "ellipse_spans", "flattenDetection", "combine_heatmap",
            "getPtsFromHeatmap", "get_pts_from_heatmap_device", "sample_desc_from_points",
            "sample_desc_device", "sample_desc_batch_device", "nn_match_pairs_device", "ha_aggregate", "ha_finalize",
            "ha_warp_views"]
@@ -78,16 +78,32 @@ def compute_valid_mask(image_shape, inv_homography, device=None, erosion_radius=
     with torch.cuda.device(dev):
         _lib.check(_lib.lib().spb_compute_valid_mask(m.data_ptr(), out.data_ptr(), m.shape[0], H, W, _stream()),
                    "compute_valid_mask")
-    if erosion_radius > 0:
-        # Same library call as the reference (cv2.erode on the host, utils/utils.py:699-702); the
-        # export path runs with radius 0 (datasets/Coco.py:31-35), so this stays off the hot path.
-        import cv2
-        k = cv2.getStructuringElement(cv2.MORPH_ELLIPSE, (erosion_radius * 2,) * 2)
-        host = out.cpu().numpy()
-        for i in range(host.shape[0]):
-            host[i] = cv2.erode(host[i], k, iterations=1)
-        out = torch.from_numpy(host).to(dev)
+    if erosion_radius > 0:  # utils/utils.py:699-702, on the device (spb_erode)
+        spans = ellipse_spans(erosion_radius * 2)
+        eroded = torch.empty_like(out)
+        sp = torch.as_tensor(spans, dtype=torch.int32).to(dev).contiguous()
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().spb_erode(out.data_ptr(), eroded.data_ptr(), m.shape[0], H, W, sp.data_ptr(),
+                                            len(spans), erosion_radius, erosion_radius, _stream()), "erode")
+        out = eroded
     return _back(out, device)
+
+
+def ellipse_spans(ksize: int):
+    """Rows of ``cv2.getStructuringElement(cv2.MORPH_ELLIPSE, (ksize, ksize))`` as column spans [j1, j2) -- OpenCV's
+    formula restated (half-axes r = c = ksize // 2, dx = round_half_even(c * sqrt(1 - dy^2 / r^2)), row i covers
+    [max(c - dx, 0), min(c + dx + 1, ksize))); the anchor cv2.erode uses by default is (ksize // 2, ksize // 2)."""
+    r = c = ksize // 2
+    inv_r2 = 1.0 / (float(r) * r) if r else 0.0
+    spans = []
+    for i in range(ksize):
+        dy = i - r
+        if abs(dy) <= r:
+            dx = int(np.rint(c * np.sqrt((r * r - dy * dy) * inv_r2)))
+            spans.append([max(c - dx, 0), min(c + dx + 1, ksize)])
+        else:
+            spans.append([0, 0])
+    return spans
 
 
 def ha_warp_views(imgs, mats_fwd, view_image=None):

@@ -421,3 +421,137 @@ def test_extract_batch_matches_per_image_path():
         assert k == ref.shape[1] and np.array_equal(pts[b, :k].cpu().numpy().astype(np.float64).T, ref)
         d = fe.sample_desc_from_points(dmap[b:b + 1].permute(0, 3, 1, 2).contiguous(), ref)
         assert np.abs(desc[b, :k].cpu().numpy().T - d).max() < 1e-6
+
+
+def test_point_tracker_gpu_vs_reference_golden(golden):
+    """PointTracker_b200.update with the GPU matcher on the reference's HPatches artefacts (fixture of the UNMODIFIED
+    tracker, tests/golden/make_tracker_golden.py): matches (x1, y1, x2, y2) and the tracks matrix bit-exact."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from pytorch_superpoint_b200 import PointTracker_b200
+    g = golden("tracker")
+    for i in range(7):
+        tr = PointTracker_b200(max_length=2, nn_thresh=1.0)
+        tr.update(g[f"hp{i}_p1"], g[f"hp{i}_d1"].astype(np.float32))
+        tr.update(g[f"hp{i}_p2"], g[f"hp{i}_d2"].astype(np.float32))
+        assert np.array_equal(tr.get_matches(), g[f"hp{i}_matches"])
+        assert np.array_equal(tr.get_mscores()[:2], g[f"hp{i}_mscores"][:2])
+        np.testing.assert_allclose(tr.get_mscores()[2], g[f"hp{i}_mscores"][2], atol=2e-6)
+        assert np.array_equal(tr.tracks[:, [0, 2, 3]], g[f"hp{i}_tracks"][:, [0, 2, 3]])
+    tr = PointTracker_b200(max_length=3, nn_thresh=0.9)
+    for k in range(5):
+        tr.update(g[f"seq{k}_pts"], g[f"seq{k}_desc"])
+        assert np.array_equal(tr.get_matches(), g[f"seq{k}_matches"])
+        assert np.array_equal(tr.tracks[:, [0, 2, 3, 4]], g[f"seq{k}_tracks"][:, [0, 2, 3, 4]])
+        np.testing.assert_allclose(tr.tracks[:, 1], g[f"seq{k}_tracks"][:, 1], atol=2e-6)
+
+
+def test_nn_match_pairs_and_batched_descriptor_sampling():
+    """The batched device entries (one launch per batch, no host round trip) against the per-image / per-pair ones:
+    spb_sample_desc_batch == sample_desc_from_points per image with zero rows behind the count, spb_nn_match_pairs ==
+    nn_match_two_way per pair (zero rows never match)."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from pytorch_superpoint_b200 import nn_match_two_way, ops
+    g = torch.Generator().manual_seed(3)
+    B, Hc, Wc, D, K = 4, 30, 40, 256, 300
+    coarse = torch.nn.functional.normalize(torch.randn(B, Hc, Wc, D, generator=g), dim=-1).cuda()
+    counts = torch.tensor([300, 120, 0, 257], dtype=torch.int32).cuda()
+    pts = torch.stack([torch.randint(4, 316, (B, K), generator=g).float(), torch.randint(4, 236, (B, K), generator=g).float(),
+                       torch.rand(B, K, generator=g)], dim=-1).cuda()
+    d = ops.sample_desc_batch_device(coarse, pts, counts)
+    assert tuple(d.shape) == (B, K, D)
+    for b in range(B):
+        c = int(counts[b])
+        assert (d[b, c:] == 0).all()
+        if c:
+            ref = ops.sample_desc_device(coarse[b], pts[b, :c].contiguous(), None, nhwc=True)
+            assert torch.equal(d[b, :c], ref)
+            want = O.sample_desc_from_points(coarse[b].permute(2, 0, 1)[None].cpu().numpy(),
+                                             pts[b, :c].cpu().numpy().astype(np.float64).T)
+            assert np.abs(d[b, :c].cpu().numpy().T - want).max() < 1e-6
+    i1, i2, sc, cnt = ops.nn_match_pairs_device(d[0::2], d[1::2], 0.9)
+    for p in range(2):
+        a, b_ = d[2 * p], d[2 * p + 1]
+        ca, cb = int(counts[2 * p]), int(counts[2 * p + 1])
+        ref = nn_match_two_way(a[:ca].T.contiguous(), b_[:cb].T.contiguous(), 0.9) if ca and cb else np.zeros((3, 0))
+        n = int(cnt[p])
+        assert n == ref.shape[1]
+        assert np.array_equal(i1[p, :n].cpu().numpy(), ref[0].astype(np.int32))
+        assert np.array_equal(i2[p, :n].cpu().numpy(), ref[1].astype(np.int32))
+        np.testing.assert_allclose(sc[p, :n].cpu().numpy(), ref[2], atol=1e-6)
+    with pytest.raises(ValueError):
+        ops.nn_match_pairs_device(d[0::2], d[1::2], -1.0)
+
+
+@pytest.mark.parametrize("H,W,B", [(240, 320, 1), (480, 640, 1), (240, 320, 5)])
+def test_val_model_heatmap_b200_vs_oracle(tmp_path, H, W, B):
+    """Val_model_heatmap_b200 (Val_model_heatmap.py:33-155) at the configs[0] / configs[4] shapes and on a batch:
+    heat-map vs the fp32 CPU oracle within 1e-2, points EXACTLY the reference's getPtsFromHeatmap of our heat-map,
+    sparse descriptors vs the oracle's sampling of our dense map (1e-6) and of the fp32 map (cosine >= 0.999)."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from pytorch_superpoint_b200.val_model import Val_model_heatmap_b200
+    sd = O.synthetic_state_dict("gauss2", seed=6)
+    tar = str(tmp_path / "superPointNet_170000_checkpoint.pth.tar")
+    torch.save({"n_iter": 170000, "model_state_dict": sd, "optimizer_state_dict": {}, "loss": 0.0}, tar)
+    cfg = {"name": "SuperPointNet_gauss2", "params": {}, "pretrained": tar, "nms": 4, "detection_threshold": 0.015,
+           "nn_thresh": 1.0, "subpixel": {"enable": True, "patch_size": 5}}
+    agent = Val_model_heatmap_b200(cfg, device="cuda")
+    agent.loadModel()
+    rng = np.random.RandomState(H + B)
+    x = torch.from_numpy(rng.rand(B, 1, H, W).astype(np.float32))
+    heat = agent.run(x)
+    assert isinstance(heat, np.ndarray) and heat.shape == (B, 1, H, W) and heat.dtype == np.float32
+    semi, desc = O.net_forward(O.canonical_params(sd), x)
+    assert np.abs(heat[:, 0] - O.flatten_detection(semi.numpy())).max() < 1e-2
+    pts = agent.heatmap_to_pts()
+    descs = agent.desc_to_sparseDesc()
+    assert len(pts) == B and len(descs) == B
+    ours = agent.outs["desc"].contiguous().cpu().numpy()
+    assert agent.outs["semi"].shape == (B, 65, H // 8, W // 8) and ours.shape == (B, 256, H // 8, W // 8)
+    for b in range(B):
+        assert pts[b].dtype == np.float64 and np.array_equal(pts[b], O.get_pts_from_heatmap(heat[b, 0], 0.015, 4))
+        assert descs[b].shape == (256, pts[b].shape[1]) and descs[b].dtype == np.float32
+        assert np.abs(descs[b] - O.sample_desc_from_points(ours[b:b + 1], pts[b])).max() < 1e-6
+        ref_d = O.sample_desc_from_points(desc.numpy()[b:b + 1], pts[b])
+        assert (descs[b] * ref_d).sum(0).min() > 0.999
+    sub = agent.soft_argmax_points(pts, patch_size=5)
+    assert len(sub) == 1 and np.abs(sub[0] - O.soft_argmax_points(heat[0, 0], pts[0], 5)).max() < 1e-4
+
+
+def test_export_descriptor_b200_writes_reference_npz(tmp_path):
+    """export.py:70-192 drop-in on 480x640 pairs (configs[4] shape): the reference's keys, shapes and dtypes; the
+    matches are EXACTLY those of the reference tracker logic (oracle matcher) on the written points / descriptors."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from pytorch_superpoint_b200 import SuperPointNet_b200
+    from pytorch_superpoint_b200.val_model import export_descriptor_b200
+    sd = O.synthetic_state_dict("gauss2", seed=8)
+    net = SuperPointNet_b200()
+    net.load_state_dict(sd)
+    rng = np.random.RandomState(2)
+    H, W = 480, 640
+    samples = []
+    for i in range(2):
+        img = rng.rand(1, 1, H, W).astype(np.float32)
+        warped = np.roll(img, (3, -5), axis=(2, 3)) * 0.9 + 0.05  # a second view of the same content
+        samples.append({"image": torch.from_numpy(img), "warped_image": torch.from_numpy(warped),
+                        "homography": torch.eye(3)[None]})
+    cfg = {"model": {"name": "SuperPointNet_gauss2", "params": {}, "pretrained": "", "nms": 4,
+                     "detection_threshold": 0.015, "nn_thresh": 1.0, "subpixel": {"enable": False, "patch_size": 5}},
+           "data": {"dataset": "hpatches"}}
+    assert export_descriptor_b200(cfg, str(tmp_path), loader=samples, net=net) == 2
+    for i in range(2):
+        f = np.load(os.path.join(str(tmp_path), "predictions", f"{i}.npz"))
+        assert sorted(f.files) == sorted(["image", "prob", "desc", "warped_image", "warped_prob", "warped_desc",
+                                          "homography", "matches"])
+        K1, K2 = f["prob"].shape[0], f["warped_prob"].shape[0]
+        assert f["image"].shape == (H, W) and f["prob"].shape == (K1, 3) and f["prob"].dtype == np.float64
+        assert f["desc"].shape == (K1, 256) and f["desc"].dtype == np.float32 and f["warped_desc"].shape == (K2, 256)
+        assert f["homography"].shape == (3, 3) and f["matches"].shape[1] == 4 and f["matches"].dtype == np.float64
+        assert np.all(np.diff(f["prob"][:, 2]) <= 0) and K1 > 0 and K2 > 0
+        assert np.abs(np.linalg.norm(f["desc"], axis=1) - 1).max() < 1e-5
+        m = O.nn_match_two_way(f["desc"].T, f["warped_desc"].T, 1.0)
+        want = np.concatenate((f["prob"][:, :2].T[:, m[0].astype(int)], f["warped_prob"][:, :2].T[:, m[1].astype(int)]))
+        assert np.array_equal(f["matches"], want.T)

@@ -56,6 +56,25 @@ def test_valid_mask_full_size_vs_reference(spb, golden):
     assert int((m != ref).sum()) <= 8
 
 
+def test_valid_mask_erosion_on_device_vs_reference(spb, golden):
+    """utils/utils.py:699-702 on the GPU (spb_erode, no host round trip): the reference's own known-answer artefact
+    notebooks/h2.npz (erosion 3 -> space-to-depth -> product over the cell, test/sample_homography.py:85-113) and
+    cv2.erode itself for radii 1..6 on random masks (border handling, even-sized elliptic element, anchor)."""
+    import cv2
+    g = golden("ref_h2")
+    inv = torch.inverse(torch.tensor(g["homographies"], dtype=torch.float32))[None]  # as the oracle's KAT test
+    m = spb.compute_valid_mask((240, 320), inv.cuda(), erosion_radius=3)
+    assert m.is_cuda
+    cells = m[0].cpu().numpy().reshape(30, 8, 40, 8).transpose(0, 2, 1, 3).reshape(30, 40, 64).prod(-1)
+    assert np.array_equal(cells[None], g["masks"])
+    _, mats = _mats(6, 12)
+    for r in range(1, 7):
+        plain = spb.compute_valid_mask((72, 104), torch.from_numpy(mats).cuda()).cpu().numpy()
+        got = spb.compute_valid_mask((72, 104), torch.from_numpy(mats).cuda(), erosion_radius=r).cpu().numpy()
+        k = cv2.getStructuringElement(cv2.MORPH_ELLIPSE, (2 * r, 2 * r))
+        assert np.array_equal(got, np.stack([cv2.erode(p, k, iterations=1) for p in plain]))
+
+
 def test_warp_degenerate_homography(spb):
     """w -> 0 / NaN coordinates must produce zeros (zero padding), not crash."""
     M = np.stack([np.eye(3), np.array([[1, 0, 0], [0, 1, 0], [1.0, 0, 0]]), np.zeros((3, 3))]).astype(np.float32)

@@ -133,3 +133,49 @@ def test_ha_end_to_end(golden):
     a = {(int(x), int(y)) for x, y, _ in pts}
     b = {(int(x), int(y)) for x, y, _ in g["pts"]}
     assert len(a & b) >= 0.98 * max(len(a | b), 1)
+
+
+class _OracleTracker:
+    """PointTracker_b200 with the CPU oracle's matcher injected: checks the host-side track bookkeeping without a GPU."""
+
+    def __new__(cls, *a, **k):
+        from pytorch_superpoint_b200.tracker import PointTracker_b200
+
+        class T(PointTracker_b200):
+            def nn_match_two_way(self, desc1, desc2, nn_thresh):
+                m = O.nn_match_two_way(np.asarray(desc1, np.float32), np.asarray(desc2, np.float32), nn_thresh)
+                self.mscores = m
+                return m
+
+        return T(*a, **k)
+
+
+def test_point_tracker_update_vs_reference_golden(golden):
+    """models/model_wrap.py:507-605 (update / get_matches / get_tracks / get_offsets): the 7 HPatches prediction files
+    the reference ships (fixture: 220 points per image, fp16 descriptors, matches of the UNMODIFIED tracker) and a
+    5-frame sequence with max_length 3 -- matches, scores and the tracks matrix bit for bit."""
+    g = golden("tracker")
+    for i in range(7):
+        tr = _OracleTracker(max_length=2, nn_thresh=1.0)
+        tr.update(g[f"hp{i}_p1"], g[f"hp{i}_d1"].astype(np.float32))
+        assert tr.get_matches().shape == (3, 0)  # first frame: nothing to match against
+        tr.update(g[f"hp{i}_p2"], g[f"hp{i}_d2"].astype(np.float32))
+        assert np.array_equal(tr.get_matches(), g[f"hp{i}_matches"]) and tr.get_matches().shape[0] == 4
+        assert np.array_equal(tr.get_mscores(), g[f"hp{i}_mscores"])
+        assert np.array_equal(tr.tracks, g[f"hp{i}_tracks"])
+        tr.clear_desc()
+        assert tr.last_desc is None
+    tr = _OracleTracker(max_length=3, nn_thresh=0.9)
+    for k in range(5):
+        tr.update(g[f"seq{k}_pts"], g[f"seq{k}_desc"])
+        assert np.array_equal(tr.tracks, g[f"seq{k}_tracks"]), k
+        assert np.array_equal(tr.get_matches(), g[f"seq{k}_matches"])
+        assert np.array_equal(tr.get_offsets(), g[f"seq{k}_offsets"])
+        assert np.array_equal(tr.get_tracks(2), g[f"seq{k}_long"])
+    assert tr.track_count == int(g["seq_count"])
+    with pytest.raises(ValueError):
+        tr.get_tracks(0)
+    with pytest.raises(ValueError):
+        _OracleTracker(max_length=1)
+    tr.update(None, None)  # models/model_wrap.py:514-516: warning, no state change
+    assert np.array_equal(tr.tracks, g["seq4_tracks"])
