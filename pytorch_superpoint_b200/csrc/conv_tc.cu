@@ -1093,13 +1093,13 @@ extern "C" int spb_conv1_fused_set_probe(long long* dev_buf) {  // debug: timeli
   return SPB_OK;
 }
 long long* conv1_probe_buf() { return g_conv1_dbg; }
-// conv1a fused into conv1b's kernel: 0 two kernels (A/B tests), 1 shifted-window conv1b (conv1_fused_kernel),
-// 2 column-stacked N=192 conv1b (conv1_s3.cu), 3 two column taps stacked, N=128 + N=64 (conv1_n128.cu);
-// set_fuse1(-1) restores the default
+// conv1a fused into conv1b's kernel: 0 two kernels (A/B tests), 1 the fused block; set_fuse1(-1) restores the default.
+// (Three other fused designs were built, measured slower and removed from the library: column-stacked N = 192 and
+// N = 128 + 64 in round 1, weight-stationary tile pairs -- tools/experiments/conv1_ws.cu -- in round 2)
 constexpr int kFuse1Default = 1;
 static int g_fuse1 = kFuse1Default;
 extern "C" int spb_conv_tc_set_fuse1(int on) {
-  g_fuse1 = on < 0 ? kFuse1Default : on > 3 ? 3 : on;
+  g_fuse1 = on < 0 ? kFuse1Default : on > 1 ? 1 : on;
   return SPB_OK;
 }
 bool conv1_fused_enabled() { return g_fuse1 != 0; }
@@ -1112,8 +1112,6 @@ int conv1_fused(const LayerDev& L1a, const LayerDev& L1b, const float* x, __nv_b
     set_error("conv1_fused: needs even H and W %% 4 == 0 (got %dx%d)", H, W);
     return SPB_EINVAL;
   }
-  if (g_fuse1 == 2) return conv1_s3(L1a, L1b, x, out, V, H, W, st);
-  if (g_fuse1 == 3) return conv1_n128(L1a, L1b, x, out, V, H, W, st);
   CUtensorMap tm_w2;
   memcpy(&tm_w2, L1b.tmap_w, sizeof(tm_w2));
   Conv1FusedArgs a;

@@ -86,11 +86,4 @@ bool conv_s3_enabled();
 int conv_s3_prepare(LayerDev& L);  // after w_s3 is uploaded
 int conv_s3(const LayerDev& L, const __nv_bfloat16* in, __nv_bfloat16* out, int B, int H, int W, cudaStream_t st);
 long long* conv1_probe_buf();  // timeline probe buffer set with spb_conv1_fused_set_probe, or NULL
-// conv1_n128.cu (conv1a + conv1b + pool, conv1b with two column taps stacked: N = 128 + N = 64)
-int conv1_n128(const LayerDev& L1a, const LayerDev& L1b, const float* x, __nv_bfloat16* out, int V, int H, int W,
-               cudaStream_t st);
-// conv1_s3.cu (conv1a + conv1b + pool, conv1b with N = 192 column-tap stacking)
-int conv1_s3(const LayerDev& L1a, const LayerDev& L1b, const float* x, __nv_bfloat16* out, int V, int H, int W,
-             cudaStream_t st);
-
 }  // namespace spb

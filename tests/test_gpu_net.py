@@ -279,53 +279,6 @@ def test_conv1_fused_block_equals_two_kernels(net, B, H, W):
     assert (d0 - d1).abs().max().item() <= 1e-6
 
 
-@pytest.mark.parametrize("B,H,W", [(1, 16, 8), (2, 24, 40), (3, 64, 96), (2, 240, 320), (1, 40, 24), (5, 120, 160)])
-def test_conv1_s3_block_equals_two_kernels(net, B, H, W):
-    """conv1a+conv1b+pool fused with the column-stacked (N=192) conv1b == conv1a kernel + conv_s3 kernel: the same
-    bf16 conv1a output and the same accumulation order, so the results must agree to fp32 rounding of the heads."""
-    from pytorch_superpoint_b200 import _lib
-    L = _lib.lib()
-    x = torch.rand(B, 1, H, W, device="cuda", generator=torch.Generator("cuda").manual_seed(W))
-    net.set_impl("tcgen05")
-    try:
-        L.spb_conv_tc_set_fuse1(0)
-        s0, d0 = net.forward_nhwc(x)
-        s0, d0 = s0.clone(), d0.clone()
-        L.spb_conv_tc_set_fuse1(2)
-        s1, d1 = net.forward_nhwc(x)
-    finally:
-        L.spb_conv_tc_set_fuse1(-1)
-    assert torch.isfinite(s1).all()
-    assert (s0 - s1).abs().max().item() <= 1e-5
-    assert (d0 - d1).abs().max().item() <= 1e-6
-
-
-@pytest.mark.parametrize("B,H,W", [(1, 16, 8), (2, 24, 40), (3, 64, 96), (2, 240, 320), (1, 40, 24), (5, 120, 160)])
-def test_conv1_n128_block_close_to_shifted_window_block(net, B, H, W):
-    """conv1a+conv1b+pool with two column taps stacked (N=128 + N=64) vs the shifted-window fused block: the same bf16
-    conv1a output, but conv1b's fp32 partial sums are accumulated in a different order (s=0 and s=2 taps share an
-    accumulator), so a few conv1b outputs round to the neighbouring bf16 value; the heads must agree to a fraction
-    of the 1e-2 heat-map tolerance."""
-    from pytorch_superpoint_b200 import _lib
-    L = _lib.lib()
-    x = torch.rand(B, 1, H, W, device="cuda", generator=torch.Generator("cuda").manual_seed(W))
-    net.set_impl("tcgen05")
-    try:
-        L.spb_conv_tc_set_fuse1(1)
-        s0, d0 = net.forward_nhwc(x)
-        s0, d0 = s0.clone(), d0.clone()
-        L.spb_conv_tc_set_fuse1(3)
-        s1, d1 = net.forward_nhwc(x)
-        s1, d1 = s1.clone(), d1.clone()
-    finally:
-        L.spb_conv_tc_set_fuse1(-1)
-    assert torch.isfinite(s1).all() and torch.isfinite(d1).all()
-    es, ed = (s0 - s1).abs(), (d0 - d1).abs()
-    scale = s0.abs().max().item()
-    assert es.max().item() <= 2e-2 * scale and es.mean().item() <= 1e-3 * scale, (es.max().item(), es.mean().item(), scale)
-    assert ed.max().item() <= 2e-2 and ed.mean().item() <= 1e-3, (ed.max().item(), ed.mean().item())
-
-
 @pytest.mark.parametrize("H,W,N", [(384, 1248, 3), (480, 640, 4), (120, 160, 7)])
 def test_ha_other_config_shapes_vs_oracle(H, W, N):
     """BASELINE configs 3-5 shapes (KITTI 384x1248, HPatches 480x640): whole HA step vs the fp32 CPU oracle --

@@ -1,11 +1,11 @@
-"""A/B of the fused first-block variants on the whole detector forward: spb_conv_tc_set_fuse1(1) vs (mode), outputs
-compared and both timed with CUDA events.   python tools/ab_fuse1.py [mode=3] [views=800]"""
+"""A/B of first-block variants on the whole detector forward: spb_conv_tc_set_fuse1(1) vs (mode; 0 = two kernels), outputs
+compared and both timed with CUDA events.   python tools/ab_fuse1.py [mode=0] [views=800]"""
 import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from pytorch_superpoint_b200 import SuperPointNet_b200, _lib
 from pytorch_superpoint_b200.synthetic import synthetic_state_dict
-mode = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+mode = int(sys.argv[1]) if len(sys.argv) > 1 else 0
 views = int(sys.argv[2]) if len(sys.argv) > 2 else 800
 L = _lib.lib()
 net = SuperPointNet_b200(); net.load_state_dict(synthetic_state_dict("gauss2", 1))

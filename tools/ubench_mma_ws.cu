@@ -124,6 +124,16 @@ __global__ void __launch_bounds__(128, 1) bench(long long* res, uint32_t* dump, 
               mma_a_use(tmem + 64, adesc(0, kk), bdesc((tap + 1) % 9, kk), idesc, acc);
               mma_a_last(tmem + 128, adesc(0, kk), bdesc((tap + 2) % 9, kk), idesc, acc);
               mma_ss(tmem + 192, adesc(3, kk), bdesc(tap, kk), idesc, acc);
+            } else if (V == 6) {  // W2 with a foreign plain MMA (other operands, other columns) between fill and lastuse
+              mma_ws_fill(tmem, adesc(0, kk), bdesc(tap, kk), idesc, acc);
+              mma_ss(tmem + 128, adesc(2, kk), bdesc((tap + 4) % 9, kk), idesc, acc);
+              mma_ws_last(tmem + 64, adesc(1, kk), bdesc(tap, kk), idesc, acc);
+              mma_ss(tmem + 192, adesc(3, kk), bdesc(tap, kk), idesc, acc);
+            } else if (V == 7) {  // reference for W6, plain
+              mma_ss(tmem, adesc(0, kk), bdesc(tap, kk), idesc, acc);
+              mma_ss(tmem + 128, adesc(2, kk), bdesc((tap + 4) % 9, kk), idesc, acc);
+              mma_ss(tmem + 64, adesc(1, kk), bdesc(tap, kk), idesc, acc);
+              mma_ss(tmem + 192, adesc(3, kk), bdesc(tap, kk), idesc, acc);
             } else if (V == 5) {  // reference for W4's accumulators, plain
               mma_ss(tmem, adesc(0, kk), bdesc(tap, kk), idesc, acc);
               mma_ss(tmem + 64, adesc(0, kk), bdesc((tap + 1) % 9, kk), idesc, acc);
@@ -164,7 +174,7 @@ __global__ void __launch_bounds__(128, 1) bench(long long* res, uint32_t* dump, 
   }
 }
 
-static uint32_t* g_dump[6];
+static uint32_t* g_dump[8];
 
 template <int V>
 static void run(const char* name, int tiles, int grid, bool keep) {
@@ -213,6 +223,9 @@ int main() {
   run<3>("W3 .ws fill + 2 use + lastuse", 1, 1, true);
   run<4>("W4 A fill / use / lastuse x 3 weight blocks", 1, 1, true);
   run<5>("W5 reference for W4 (plain)", 1, 1, true);
+  run<6>("W6 .ws fill / foreign plain MMA / lastuse", 1, 1, true);
+  run<7>("W7 reference for W6 (plain)", 1, 1, true);
+  compare(7, 6, "W6 vs W7 (a plain MMA between fill and lastuse)");
   compare(0, 1, "W1 vs W0");
   compare(0, 2, "W2 vs W0");
   compare(0, 3, "W3 vs W0");
@@ -224,6 +237,7 @@ int main() {
     run<2>("W2 .ws, B fill + lastuse (2 tiles per weight block)", tiles, grid, false);
     run<3>("W3 .ws, B fill + use + use + lastuse (4 tiles per weight block)", tiles, grid, false);
     run<4>("W4 A fill + use + lastuse (3 weight blocks per A) + 1 plain", tiles, grid, false);
+    run<6>("W6 .ws fill / plain / lastuse / plain", tiles, grid, false);
   }
   return 0;
 }
