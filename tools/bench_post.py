@@ -15,7 +15,14 @@ from pytorch_superpoint_b200 import ops  # noqa: E402
 from pytorch_superpoint_b200.homographies import sample_ha_homographies_device  # noqa: E402
 
 
+ONCE = False
+
+
 def timed(fn, n=20):
+    if ONCE:  # ncu target: every kernel exactly once
+        fn()
+        torch.cuda.synchronize()
+        return float("nan")
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
@@ -34,7 +41,10 @@ def main():
     ap.add_argument("--W", type=int, default=320)
     ap.add_argument("--B", type=int, default=32)
     ap.add_argument("--K", type=int, default=1000)
+    ap.add_argument("--once", action="store_true", help="run every operator once (the ncu capture target)")
     a = ap.parse_args()
+    global ONCE
+    ONCE = a.once
     dev = torch.device("cuda", 0)
     g = torch.Generator(device="cpu").manual_seed(0)
     H, W, B, K = a.H, a.W, a.B, a.K
@@ -49,10 +59,12 @@ def main():
     print("  mean key-points", float(counts.float().mean()))
     D, Hc, Wc = 256, H // 8, W // 8
     coarse = torch.nn.functional.normalize(torch.randn((B, Hc, Wc, D), generator=g), dim=-1).to(dev)
-    if hasattr(ops, "sample_desc_batch_device"):
-        ms = timed(lambda: ops.sample_desc_batch_device(coarse, pts, counts))
-        kk = float(counts.sum())
-        print(f"sample_desc (batched) B={B} K<={K}: {ms:.4f} ms -> {kk * D * 4 * 5 / ms / 1e6:.1f} GB/s (4 taps read + 1 write)")
+    ms = timed(lambda: ops.sample_desc_batch_device(coarse, pts, counts))
+    kk = float(counts.sum())
+    print(f"sample_desc (batched) B={B} K<={K}: {ms:.4f} ms -> {kk * D * 4 * 5 / ms / 1e6:.1f} GB/s (4 taps read + 1 write)")
+    dd = ops.sample_desc_batch_device(coarse, pts, counts)
+    ms = timed(lambda: ops.nn_match_pairs_device(dd[0::2], dd[1::2], 0.7))
+    print(f"nn_match_pairs {B // 2} pairs x {K}x{K}, no host round trip: {ms:.4f} ms -> {B // 2 * 2 * K * K * D / ms / 1e9:.3f} TFLOP/s")
     ms = timed(lambda: ops.sample_desc_device(coarse[0], pts[0], counts[0:1], nhwc=True))
     k0 = int(counts[0])
     print(f"sample_desc (one image, K={k0}): {ms:.4f} ms -> {k0 * D * 4 * 5 / ms / 1e6:.1f} GB/s")

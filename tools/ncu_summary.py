@@ -22,9 +22,9 @@ METRICS = [
     ("launch__registers_per_thread", "registers/thread"),
     ("launch__grid_size", "grid"),
     ("launch__block_size", "block"),
-    ("sm__inst_executed_pipe_tensor.avg.pct_of_peak_sustained_active", "tensor pipe %"),
-    ("sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_elapsed", "tensor (hmma) active % elapsed"),
-    ("l1tex__data_pipe_tc_wavefronts_mem_shared.avg.pct_of_peak_sustained_elapsed", "smem operand-read pipe %"),
+    ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "tensor pipe active % (elapsed)"),
+    ("l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "smem operand-read pipe %"),
+    ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "smem LSU wavefronts %"),
     ("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "lsu pipe %"),
     ("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "xu pipe %"),
 ]
