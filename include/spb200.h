@@ -130,6 +130,11 @@ int spb_roi_soft_argmax(const float* heat, int B, int H, int W, const long long*
  * coarse NHWC [B,Hc,Wc,D] fp32 (D % 8 == 0, D <= 256) -> dense NCHW [B,D,Hc*cell,Wc*cell] fp32. */
 int spb_dense_desc(const float* coarse_nhwc, int B, int Hc, int Wc, int D, int cell, float* dense_nchw, void* stream);
 
+/* models/model_wrap.py:402-404: the dense map's columns at the integer key-points of every image (one launch):
+ * dense NCHW [B,D,H,W], pts [B,K,3], counts [B] (device) -> out [B,K,D]; rows behind counts[b] are left untouched. */
+int spb_gather_dense_desc(const float* dense_nchw, const float* pts, const int* counts, int B, int K, int D, int H, int W,
+                          float* out, void* stream);
+
 /* NEXT row f-1b -- models/model_wrap.py:200-234 `soft_argmax_points` (+ utils/losses.py:48-129): per key-point
  * soft-argmax offset over the patch_size x patch_size (odd, <= 7) heat-map patch.  dxdy [K,2] fp32; the
  * refined point is (x + dx - patch_size/2, y + dy - patch_size/2).  torchgeometry's SpatialSoftArgmax2d is

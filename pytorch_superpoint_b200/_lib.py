@@ -37,6 +37,7 @@ PROTOTYPES = {
     "spb_sample_desc_from_points": (_i, [_p, _i, _p, _p, _i, _i, _i, _i, _i, _p, _p]),
     "spb_sample_desc_from_points_ex": (_i, [_p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _p, _p]),
     "spb_roi_soft_argmax": (_i, [_p, _i, _i, _i, _p, _i, _p, _p, _p]),
+    "spb_gather_dense_desc": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p, _p]),
     "spb_dense_desc": (_i, [_p, _i, _i, _i, _i, _i, _p, _p]),
     "spb_soft_argmax_points": (_i, [_p, _i, _i, _p, _p, _i, _i, _p, _p]),
     "spb_soft_argmax_points_batch": (_i, [_p, _i, _i, _i, _p, _p, _i, _i, _p, _p]),

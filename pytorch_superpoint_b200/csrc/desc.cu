@@ -93,6 +93,34 @@ extern "C" int spb_sample_desc_from_points(const float* coarse, int nhwc, const 
   return spb_sample_desc_from_points_ex(coarse, nhwc, pts, 3, count, K, Hc, Wc, D, cell, 1, out, stream);
 }
 
+// models/model_wrap.py:402-404 (`dense_desc_cpu[i, :, pts[1], pts[0]]`): the columns of the dense descriptor map at the
+// integer key-points of every image, one launch for the batch.  dense NCHW [B,D,H,W], pts [B,K,3], counts [B] ->
+// out [B,K,D] (rows behind counts[b] untouched).
+namespace spb {
+__global__ void __launch_bounds__(256) gather_dense_kernel(const float* __restrict__ dense, const float* __restrict__ pts,
+                                                           const int* __restrict__ counts, int K, int D, int H, int W,
+                                                           float* __restrict__ out) {
+  const int lane = threadIdx.x & 31, k = blockIdx.x * 8 + (threadIdx.x >> 5), b = blockIdx.y;
+  if (k >= min(counts[b], K)) return;
+  const float* p = pts + ((long long)b * K + k) * 3;
+  const int x = min(max((int)p[0], 0), W - 1), y = min(max((int)p[1], 0), H - 1);
+  const float* src = dense + (long long)b * D * H * W + (long long)y * W + x;
+  float* o = out + ((long long)b * K + k) * D;
+  for (int c = lane; c < D; c += 32) o[c] = __ldg(src + (long long)c * H * W);
+}
+}  // namespace spb
+
+extern "C" int spb_gather_dense_desc(const float* dense_nchw, const float* pts, const int* counts, int B, int K, int D,
+                                     int H, int W, float* out, void* stream) {
+  SPB_CHECK_ARG(dense_nchw && pts && counts && out);
+  SPB_CHECK_ARG(B >= 0 && B <= 65535 && K >= 0 && D >= 1 && H >= 1 && W >= 1);
+  if (B == 0 || K == 0) return SPB_OK;
+  dim3 grid(spb::ceil_div(K, 8), B);
+  spb::gather_dense_kernel<<<grid, 256, 0, spb::as_stream(stream)>>>(dense_nchw, pts, counts, K, D, H, W, out);
+  SPB_CHECK_LAUNCH();
+  return SPB_OK;
+}
+
 // ---- sub-pixel refinement (NEXT row f-1b): models/model_wrap.py:200-234 + utils/losses.py:48-129 ------------
 // One thread per key-point: zero-padded PxP patch centred on the integer key-point, p/(sum p + 1e-6), negatives ->
 // 1e-6, log, spatial soft-argmax in pixel coordinates sum(pos*e)/(sum e + 1e-6) (torchgeometry 0.1.x

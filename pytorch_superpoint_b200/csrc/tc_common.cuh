@@ -25,11 +25,19 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok = 0;
   const long long t0 = clock64();
   while (true) {
+#ifdef SPB_MBAR_HINT_NS  // A/B: let the hardware suspend the waiting thread for up to this many ns per try
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\nselp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"((uint32_t)SPB_MBAR_HINT_NS)
+        : "memory");
+#else
     asm volatile(
         "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
         : "=r"(ok)
         : "r"(bar), "r"(parity)
         : "memory");
+#endif
     if (ok) return;
     // (a __nanosleep here was measured: 20 / 100 ns back-off costs 1.5 % of throughput, no power-cap relief)
     if (clock64() - t0 > 4000000000LL) {

@@ -137,25 +137,26 @@ class SuperPointFrontend_b200(object):
         self.heatmap = heat
         if onlyHeatmap:
             return heat
-        p, counts, _ = ops.get_pts_from_heatmap_device(heat[:, 0], self.conf_thresh, self.nms_dist, self.border_remove)
-        counts = counts.cpu().numpy()
-        p = p.cpu().numpy().astype(np.float64)
-        pts = [p[i, :counts[i]].T.copy() for i in range(B)]
-        self.pts = pts
-        # models/model_wrap.py:393-404: dense = normalise(interpolate(coarse, x8)); one fused kernel, and only the
-        # key-point columns (not the 78 MB/image dense tensor) travel to the host
+        p_dev, c_dev, _ = ops.get_pts_from_heatmap_device(heat[:, 0], self.conf_thresh, self.nms_dist, self.border_remove)
+        # models/model_wrap.py:393-404: dense = normalise(interpolate(coarse, x8)) in one fused kernel; the key-point
+        # columns of all images are gathered in one launch, and only they (not the 78 MB/image dense tensor) travel
         D = desc.shape[-1]
         dense = torch.empty((B, D, H, W), device=dev, dtype=torch.float32)
+        cols = torch.empty((B, p_dev.shape[1], D), device=dev, dtype=torch.float32)
+        L = _lib.lib()
         with torch.cuda.device(dev):
-            _lib.check(_lib.lib().spb_dense_desc(desc.data_ptr(), B, H // self.cell, W // self.cell, D, self.cell,
-                                                 dense.data_ptr(), torch.cuda.current_stream().cuda_stream),
-                       "dense_desc")
-        pts_desc = []
-        for i in range(B):
-            yy = torch.as_tensor(pts[i][1, :].astype(np.int64), device=dev)
-            xx = torch.as_tensor(pts[i][0, :].astype(np.int64), device=dev)
-            # (numpy's dense_cpu[i, :, ys, xs].transpose() in the reference comes out as [D, K]; same here)
-            pts_desc.append(dense[i][:, yy, xx].cpu().numpy())
+            st = torch.cuda.current_stream().cuda_stream
+            _lib.check(L.spb_dense_desc(desc.data_ptr(), B, H // self.cell, W // self.cell, D, self.cell,
+                                        dense.data_ptr(), st), "dense_desc")
+            _lib.check(L.spb_gather_dense_desc(dense.data_ptr(), p_dev.data_ptr(), c_dev.data_ptr(), B, p_dev.shape[1], D,
+                                               H, W, cols.data_ptr(), st), "gather_dense_desc")
+        counts = c_dev.cpu().numpy()
+        p = p_dev.cpu().numpy().astype(np.float64)
+        cols = cols.cpu().numpy()
+        pts = [p[i, :counts[i]].T.copy() for i in range(B)]
+        self.pts = pts
+        # (numpy's dense_cpu[i, :, ys, xs].transpose() in the reference comes out as [D, K]; same here)
+        pts_desc = [cols[i, :counts[i]].T.copy() for i in range(B)]
         if self.subpixel:
             raise NotImplementedError("residual sub-pixel head (SubpixelNet) is outside the hot path")
         return pts, pts_desc, dense, heat

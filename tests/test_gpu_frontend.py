@@ -555,3 +555,42 @@ def test_export_descriptor_b200_writes_reference_npz(tmp_path):
         m = O.nn_match_two_way(f["desc"].T, f["warped_desc"].T, 1.0)
         want = np.concatenate((f["prob"][:, :2].T[:, m[0].astype(int)], f["warped_prob"][:, :2].T[:, m[1].astype(int)]))
         assert np.array_equal(f["matches"], want.T)
+
+
+def test_export_kitti_shape_full_views_vs_oracle():
+    """BASELINE configs[3] at full size: ONE 384x1248 image with all 100 homographies through HAExporter -- the pass
+    size is bounded by bytes (128 views at this shape), the workspace is sized for the fused first block -- against the
+    CPU oracle: heat-map within 1e-2, key-points exactly the reference's NMS / top-k of our heat-map."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from pytorch_superpoint_b200 import SuperPointNet_b200, _lib, make_ha_homographies
+    from pytorch_superpoint_b200.export import HAExporter
+    H, W, N = 384, 1248, 100
+    rng = np.random.RandomState(3)
+    img = np.full((H, W), 0.35, np.float32) + 0.03 * rng.randn(H, W).astype(np.float32)
+    for _ in range(30):
+        x0, y0 = rng.randint(0, W - 10), rng.randint(0, H - 10)
+        img[y0:y0 + rng.randint(8, H // 3), x0:x0 + rng.randint(8, W // 4)] = rng.uniform(0, 1)
+    img = np.clip(img, 0, 1)
+    mu, mf = make_ha_homographies(N, seed=5)
+    sd = O.synthetic_state_dict("gauss2", seed=1)
+    net = SuperPointNet_b200()
+    net.load_state_dict(sd)
+    exp = HAExporter(net, 0.015, 4, 600)
+    assert net.ha_pass_views(H, W) == 128
+    plan, _ = exp.plan(1, N, H, W, True)
+    assert len(plan.passes) == 1 and plan.passes[0].num_views == N
+    L = _lib.lib()
+    assert L.spb_ha_workspace_bytes_ragged(1, N, N, H, W) < 12 * (1 << 30)  # (round 1 sized 49 GB for the same pass)
+    pts = exp.export_batch([torch.from_numpy(img)], torch.from_numpy(mu), torch.from_numpy(mf))[0]
+    heat = exp.last_heat(1, H, W)[0].cpu().numpy()
+    ref_pts, ref_heat = O.ha_export_one(img, mu, mf, O.canonical_params(sd), return_heat=True)
+    assert np.isfinite(heat).all() and np.abs(heat - ref_heat).max() < 1e-2
+    assert np.array_equal(pts, O.get_pts_from_heatmap(heat, 0.015, 4).T[:600])
+    # a smaller pass size splits the image's views into accumulating slices: same sums up to fp32 order
+    small = HAExporter(net, 0.015, 4, 600, chunk=48)
+    plan2, _ = small.plan(1, N, H, W, True)
+    assert [p.num_views for p in plan2.passes] == [48, 48, 4] and [p.accumulate for p in plan2.passes] == [False, True, True]
+    small.export_batch([torch.from_numpy(img)], torch.from_numpy(mu), torch.from_numpy(mf))
+    heat2 = small.last_heat(1, H, W)[0].cpu().numpy()
+    assert np.abs(heat2 - heat).max() < 1e-5
