@@ -173,6 +173,13 @@ int spb_sample_ha_homographies(unsigned long long seed, int total, int per_image
                                double max_angle, int allow_artifacts, double translation_overflow,
                                float* homographies, float* inv_homographies, float* raw_or_null, void* stream);
 
+/* NEXT row f-4 (image ingest) -- datasets/Coco.py:165-179 `_read_image` behind the JPEG decode:
+ * `cv2.resize(img, (W, H), interpolation=cv2.INTER_AREA)` -> `cv2.cvtColor(img, cv2.COLOR_RGB2GRAY)` (applied to
+ * imread's BGR memory order, as the reference does) -> `astype(float32) / 255`.  bgr: DEVICE uint8 [Hs,Ws,3]; out
+ * fp32 [H,W] in [0,1].  Bit-exact against OpenCV 4.x for down-scaling (Hs >= H and Ws >= W: integer factors through
+ * its box-sum arithmetic, the rest through its per-axis cell tables); enlarging an axis is SPB_EINVAL. */
+int spb_ingest_resize_gray(const uint8_t* bgr, int Hs, int Ws, float* out, int H, int W, void* stream);
+
 /* ---- (2) network ------------------------------------------------------------------------------------
  * models/SuperPointNet_pretrained.py:46-76, SuperPointNet_gauss2.py:43-70, SuperPointNet.py:154-224.
  * weights/biases: HOST pointers, 12 layers in the order conv1a,1b,2a,2b,3a,3b,4a,4b,Pa,Pb,Da,Db;

@@ -416,3 +416,70 @@ def extract_one(img: np.ndarray, params: dict, conf_thresh=0.015, nms_dist=4, bn
     heat = flatten_detection(semi.numpy())[0]
     pts = get_pts_from_heatmap(heat, conf_thresh, nms_dist)
     return pts, sample_desc_from_points(desc.numpy(), pts), heat
+
+
+# --------------------------------------------------------------------------------------
+# image ingest: datasets/Coco.py:165-179 (_read_image behind cv2.imread)
+# --------------------------------------------------------------------------------------
+def _area_tab(ssize: int, dsize: int, scale: float):
+    """OpenCV's computeResizeAreaTab (imgproc/resize.cpp): (dst index, src index, weight) entries."""
+    import math
+    tab = []
+    for dx in range(dsize):
+        fsx1 = dx * scale
+        fsx2 = fsx1 + scale
+        cell = min(scale, ssize - fsx1)
+        sx1, sx2 = math.ceil(fsx1), math.floor(fsx2)
+        sx2 = min(sx2, ssize - 1)
+        sx1 = min(sx1, sx2)
+        if sx1 - fsx1 > 1e-3:
+            tab.append((dx, sx1 - 1, f32((sx1 - fsx1) / cell)))
+        for sx in range(sx1, sx2):
+            tab.append((dx, sx, f32(1.0 / cell)))
+        if fsx2 - sx2 > 1e-3:
+            tab.append((dx, sx2, f32(min(min(fsx2 - sx2, 1.0), cell) / cell)))
+    return tab
+
+
+def resize_area_u8(src: np.ndarray, H: int, W: int) -> np.ndarray:
+    """``cv2.resize(src, (W, H), interpolation=cv2.INTER_AREA)`` for uint8 [Hs,Ws,C], down-scaling only: OpenCV's
+    resizeAreaFast_ (integer factors: box sums, (s+2)>>2 for 2x2, round-half-even of s * (1.f/area) otherwise) and
+    resizeArea_ (per-axis cell tables, fp32 products and sums in table order) restated."""
+    Hs, Ws, C = src.shape
+    sx, sy = 1.0 / (W / Ws), 1.0 / (H / Hs)
+    if sx < 1.0 or sy < 1.0:
+        raise ValueError("INTER_AREA up-scaling (OpenCV's linear variant) is not restated")
+    ix, iy = int(round(sx)), int(round(sy))
+    if abs(sx - ix) < np.finfo(np.float64).eps and abs(sy - iy) < np.finfo(np.float64).eps:
+        s = src[:H * iy, :W * ix].astype(np.int64).reshape(H, iy, W, ix, C).sum(axis=(1, 3))
+        if ix == 2 and iy == 2:
+            return ((s + 2) >> 2).astype(np.uint8)
+        return np.clip(np.rint(s.astype(f32) * (f32(1.0) / f32(ix * iy))), 0, 255).astype(np.uint8)
+    xtab, ytab = _area_tab(Ws, W, sx), _area_tab(Hs, H, sy)
+    xd = np.array([t[0] for t in xtab])
+    xs = np.array([t[1] for t in xtab])
+    xa = np.array([t[2] for t in xtab], f32)
+    dst = np.zeros((H, W, C), np.uint8)
+    acc = np.zeros((W, C), f32)
+    prev = ytab[0][0]
+    for dy, sy_i, beta in ytab:
+        row = src[sy_i].astype(f32)
+        buf = np.zeros((W, C), f32)
+        for k in range(len(xtab)):  # (entries of one destination cell are consecutive: sequential fp32 adds)
+            buf[xd[k]] = buf[xd[k]] + row[xs[k]] * xa[k]
+        if dy != prev:
+            dst[prev] = np.clip(np.rint(acc), 0, 255).astype(np.uint8)
+            acc = (beta * buf).astype(f32)
+            prev = dy
+        else:
+            acc = (acc + beta * buf).astype(f32)
+    dst[prev] = np.clip(np.rint(acc), 0, 255).astype(np.uint8)
+    return dst
+
+
+def ingest_resize_gray(img_bgr: np.ndarray, H: int, W: int) -> np.ndarray:
+    """datasets/Coco.py:170-178: INTER_AREA resize, ``cv2.COLOR_RGB2GRAY`` on imread's BGR memory order (OpenCV's 15-bit
+    fixed point: 9798, 19235, 3735), ``astype('float32') / 255``."""
+    r = resize_area_u8(np.asarray(img_bgr, np.uint8), H, W).astype(np.int64)
+    g = (r[..., 0] * 9798 + r[..., 1] * 19235 + r[..., 2] * 3735 + (1 << 14)) >> 15
+    return g.astype(f32) / f32(255.0)

@@ -48,6 +48,7 @@ PROTOTYPES = {
     "spb_nn_match_two_way": (_i, [_p, _i, _p, _i, _i, _f, _p, _p, _p, _p, _p, _z, _p]),
     "spb_sample_ha_homographies": (_i, [C.c_ulonglong, _i, _i, _i, _i, _i, _i, _i, _i, C.c_double, C.c_double, C.c_double,
                                         C.c_double, C.c_double, _i, C.c_double, _p, _p, _p, _p]),
+    "spb_ingest_resize_gray": (_i, [_p, _i, _i, _p, _i, _i, _p]),
     "spb_net_create": (_i, [C.POINTER(_p), C.POINTER(_p), C.POINTER(_p)]),
     "spb_net_destroy": (_i, [_p]),
     "spb_net_set_impl": (_i, [_p, _i]),

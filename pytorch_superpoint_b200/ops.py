@@ -17,7 +17,7 @@ from . import _lib
 __all__ = ["inv_warp_image_batch", "compute_valid_mask", "ellipse_spans", "flattenDetection", "combine_heatmap",
            "getPtsFromHeatmap", "get_pts_from_heatmap_device", "sample_desc_from_points",
            "sample_desc_device", "sample_desc_batch_device", "nn_match_pairs_device", "ha_aggregate", "ha_finalize",
-           "ha_warp_views"]
+           "ha_warp_views", "ingest_resize_gray"]
 
 
 def _dev(device=None) -> torch.device:
@@ -131,6 +131,23 @@ def ha_warp_views(imgs, mats_fwd, view_image=None):
         _lib.check(L.spb_ha_warp_views(x.data_ptr(), m.data_ptr(), vi.data_ptr(), None, nb, V, H, W, views.data_ptr(),
                                        bits.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), "ha_warp_views")
     return views, bits
+
+
+def ingest_resize_gray(img_bgr, size, device=None):
+    """datasets/Coco.py:165-179 behind ``cv2.imread``: uint8 [Hs,Ws,3] (numpy or tensor, imread's BGR order) ->
+    INTER_AREA resize to ``size`` = (H, W), OpenCV's RGB2GRAY on that memory order, float32 / 255 -> cuda fp32 [H,W].
+    Bit-exact against OpenCV for down-scaling; the uint8 image (3 bytes per source pixel) is what crosses to the GPU."""
+    dev = _dev(device if device is not None else (img_bgr.device if torch.is_tensor(img_bgr) and img_bgr.is_cuda else None))
+    x = img_bgr if torch.is_tensor(img_bgr) else torch.from_numpy(np.ascontiguousarray(img_bgr))
+    if x.dtype != torch.uint8 or x.dim() != 3 or x.shape[2] != 3:
+        raise ValueError(f"expected a uint8 [H,W,3] image, got {x.dtype} {tuple(x.shape)}")
+    x = x.to(dev).contiguous()
+    H, W = int(size[0]), int(size[1])
+    out = torch.empty((H, W), device=dev, dtype=torch.float32)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().spb_ingest_resize_gray(x.data_ptr(), x.shape[0], x.shape[1], out.data_ptr(), H, W,
+                                                     _stream()), "ingest_resize_gray")
+    return out
 
 
 def flattenDetection(semi, tensor=False):

@@ -274,3 +274,24 @@ def test_sample_desc(spb, golden):
     a = ops.sample_desc_device(c, p, nhwc=False)
     b = ops.sample_desc_device(c.permute(1, 2, 0).contiguous(), p, nhwc=True)
     assert torch.equal(a, b)
+
+
+# ---------------------------------------------------------------------------------------------- ingest
+@pytest.mark.parametrize("Hs,Ws,H,W", [(480, 640, 240, 320), (375, 500, 240, 320), (427, 640, 240, 320),
+                                       (720, 960, 240, 320), (333, 500, 120, 160), (240, 320, 240, 320),
+                                       (640, 480, 480, 480), (500, 375, 96, 64), (1080, 1920, 480, 640)])
+def test_ingest_resize_gray_equals_opencv(spb, Hs, Ws, H, W):
+    """f-4 image ingest on the GPU (ingest.cu) == cv2.resize(INTER_AREA) -> cv2.cvtColor(RGB2GRAY) -> float32 / 255,
+    bit for bit (what datasets/Coco.py:165-179 computes on the host), for integer and fractional scale factors."""
+    import cv2
+    from pytorch_superpoint_b200 import ops
+    rng = np.random.RandomState(Hs + W)
+    img = rng.randint(0, 256, (Hs, Ws, 3)).astype(np.uint8)
+    want = cv2.cvtColor(cv2.resize(img, (W, H), interpolation=cv2.INTER_AREA), cv2.COLOR_RGB2GRAY).astype("float32") / 255.0
+    got = ops.ingest_resize_gray(img, (H, W))
+    assert got.is_cuda and got.dtype == torch.float32 and tuple(got.shape) == (H, W)
+    assert np.array_equal(got.cpu().numpy(), want)
+    if Hs * Ws <= 500 * 640:
+        assert np.array_equal(got.cpu().numpy(), O.ingest_resize_gray(img, H, W))
+    with pytest.raises(RuntimeError, match="enlarges"):
+        ops.ingest_resize_gray(img[:H // 2], (H, W))

@@ -179,3 +179,21 @@ def test_point_tracker_update_vs_reference_golden(golden):
         _OracleTracker(max_length=1)
     tr.update(None, None)  # models/model_wrap.py:514-516: warning, no state change
     assert np.array_equal(tr.tracks, g["seq4_tracks"])
+
+
+@pytest.mark.parametrize("Hs,Ws,H,W", [(480, 640, 240, 320), (375, 500, 240, 320), (427, 640, 240, 320),
+                                       (720, 960, 240, 320), (333, 500, 120, 160), (240, 320, 240, 320),
+                                       (640, 480, 480, 480), (500, 375, 96, 64)])
+def test_ingest_oracle_equals_opencv(Hs, Ws, H, W):
+    """Image ingest (datasets/Coco.py:165-179 behind cv2.imread): the oracle's restatement of OpenCV's INTER_AREA
+    (integer-factor and general path) + RGB2GRAY fixed point + /255 is bit-identical to the library calls the
+    reference makes (OpenCV is the third-party arithmetic here; it IS installed, so this is pinned)."""
+    import cv2
+    rng = np.random.RandomState(Hs + W)
+    img = rng.randint(0, 256, (Hs, Ws, 3)).astype(np.uint8)
+    ref = cv2.resize(img, (W, H), interpolation=cv2.INTER_AREA)
+    assert np.array_equal(O.resize_area_u8(img, H, W), ref)
+    want = cv2.cvtColor(ref, cv2.COLOR_RGB2GRAY).astype("float32") / 255.0
+    assert np.array_equal(O.ingest_resize_gray(img, H, W), want)
+    with pytest.raises(ValueError):
+        O.resize_area_u8(img[:50, :60], 64, 64)
