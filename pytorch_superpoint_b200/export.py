@@ -89,9 +89,9 @@ class HAExporter:
             self._plans[key] = (plan, dev_passes)
         return self._plans[key]
 
-    def partial_sums(self, imgs_dev, mats_unwarp, mats_fwd, sums, plan_dev) -> None:
-        """This rank's partial (sum heat*mask, sum mask) planes of every image of the batch: warp -> detector
-        network -> aggregate, pass by pass (the ``partial_fn`` of ``sharding.sharded_heatmap_sums``)."""
+    def _partial_fn(self, imgs_dev, mats_unwarp, mats_fwd, plan_dev):
+        """The ``partial_fn`` of ``sharding.sharded_heatmap_sums``: one pass of this rank's views (warp -> detector
+        network -> aggregate) written / added into the partial (sum heat*mask, sum mask) planes of its images."""
         mu = mats_unwarp.to(self.device, torch.float32).reshape(-1, 3, 3)
         mf = mats_fwd.to(self.device, torch.float32).reshape(-1, 3, 3)
         by_pass = {id(p): t for p, *t in plan_dev}
@@ -116,7 +116,7 @@ class HAExporter:
         main = torch.cuda.current_stream()
         if slot["done"] is not None:
             main.wait_event(slot["done"])  # the exchange / side stream of two batches ago still reads this slot
-        partial_fn = self.partial_sums(imgs_dev, mats_unwarp, mats_fwd, slot["sums"], plan_dev)
+        partial_fn = self._partial_fn(imgs_dev, mats_unwarp, mats_fwd, plan_dev)
         owned, work, _ = sharded_heatmap_sums(partial_fn, B, N, slot["sums"], group=self.group, plan=plan,
                                               out=slot["owned"], async_op=True)
         ready = torch.cuda.Event()
