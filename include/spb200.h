@@ -176,8 +176,9 @@ int spb_sample_ha_homographies(unsigned long long seed, int total, int per_image
 /* NEXT row f-4 (image ingest) -- datasets/Coco.py:165-179 `_read_image` behind the JPEG decode:
  * `cv2.resize(img, (W, H), interpolation=cv2.INTER_AREA)` -> `cv2.cvtColor(img, cv2.COLOR_RGB2GRAY)` (applied to
  * imread's BGR memory order, as the reference does) -> `astype(float32) / 255`.  bgr: DEVICE uint8 [Hs,Ws,3]; out
- * fp32 [H,W] in [0,1].  Bit-exact against OpenCV 4.x for down-scaling (Hs >= H and Ws >= W: integer factors through
- * its box-sum arithmetic, the rest through its per-axis cell tables); enlarging an axis is SPB_EINVAL. */
+ * fp32 [H,W] in [0,1].  Bit-exact against OpenCV 4.x: down-scaling (Hs >= H and Ws >= W) through its box-sum
+ * arithmetic for integer factors and its per-axis cell tables otherwise; when an axis is enlarged (KITTI 375x1242 ->
+ * 384x1248) through its 11-bit fixed-point linear variant with "area" coefficients. */
 int spb_ingest_resize_gray(const uint8_t* bgr, int Hs, int Ws, float* out, int H, int W, void* stream);
 
 /* ---- (2) network ------------------------------------------------------------------------------------

@@ -441,14 +441,51 @@ def _area_tab(ssize: int, dsize: int, scale: float):
     return tab
 
 
+def _resize_area_linear_u8(src: np.ndarray, H: int, W: int) -> np.ndarray:
+    """OpenCV's INTER_AREA when an axis is enlarged: the 8-bit linear resize with "area" coefficients (imgproc/resize.cpp:
+    s = floor(d*scale), f = (float)((d+1) - (s+1)*inv_scale) reduced to its fractional part, 11-bit fixed-point
+    weights, HResizeLinear into int32, VResizeLinear (((b0*(S0>>4))>>16) + ((b1*(S1>>4))>>16) + 2) >> 2)."""
+    import math
+    Hs, Ws, C = src.shape
+
+    def axis(dsz, ssz):
+        inv = dsz / ssz
+        scale = 1.0 / inv
+        ofs, w, dmax = np.zeros(dsz, np.int64), np.zeros((dsz, 2), np.int64), dsz
+        for d in range(dsz):
+            s = math.floor(d * scale)
+            f = f32((d + 1) - (s + 1) * inv)
+            f = f32(0.0) if f <= 0 else f32(f - math.floor(f))
+            if s < 0:
+                f, s = f32(0.0), 0
+            if s + 1 >= ssz:
+                dmax = min(dmax, d)
+                if s >= ssz - 1:
+                    f, s = f32(0.0), ssz - 1
+            ofs[d] = s
+            w[d, 0] = int(np.rint(f32((f32(1.0) - f) * f32(2048.0))))
+            w[d, 1] = int(np.rint(f32(f * f32(2048.0))))
+        return ofs, w, dmax
+
+    xo, xa, xmax = axis(W, Ws)
+    yo, ya, _ = axis(H, Hs)
+    S = src.astype(np.int64)
+    rows = S[:, xo, :] * xa[None, :, 0, None] + S[:, np.minimum(xo + 1, Ws - 1), :] * xa[None, :, 1, None]
+    if xmax < W:
+        rows[:, xmax:, :] = S[:, xo[xmax:], :] * 2048
+    r0, r1 = rows[yo], rows[np.minimum(yo + 1, Hs - 1)]
+    v = (((ya[:, 0, None, None] * (r0 >> 4)) >> 16) + ((ya[:, 1, None, None] * (r1 >> 4)) >> 16) + 2) >> 2
+    return np.clip(v, 0, 255).astype(np.uint8)
+
+
 def resize_area_u8(src: np.ndarray, H: int, W: int) -> np.ndarray:
-    """``cv2.resize(src, (W, H), interpolation=cv2.INTER_AREA)`` for uint8 [Hs,Ws,C], down-scaling only: OpenCV's
-    resizeAreaFast_ (integer factors: box sums, (s+2)>>2 for 2x2, round-half-even of s * (1.f/area) otherwise) and
+    """``cv2.resize(src, (W, H), interpolation=cv2.INTER_AREA)`` for uint8 [Hs,Ws,C]: OpenCV's linear variant when an axis
+    is enlarged, else resizeAreaFast_ (integer factors: box sums, (s+2)>>2 for 2x2, round-half-even of s * (1.f/area) otherwise) and
     resizeArea_ (per-axis cell tables, fp32 products and sums in table order) restated."""
     Hs, Ws, C = src.shape
     sx, sy = 1.0 / (W / Ws), 1.0 / (H / Hs)
     if sx < 1.0 or sy < 1.0:
-        raise ValueError("INTER_AREA up-scaling (OpenCV's linear variant) is not restated")
+        return _resize_area_linear_u8(src, H, W)
     ix, iy = int(round(sx)), int(round(sy))
     if abs(sx - ix) < np.finfo(np.float64).eps and abs(sy - iy) < np.finfo(np.float64).eps:
         s = src[:H * iy, :W * ix].astype(np.int64).reshape(H, iy, W, ix, C).sum(axis=(1, 3))

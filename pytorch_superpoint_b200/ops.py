@@ -136,7 +136,7 @@ def ha_warp_views(imgs, mats_fwd, view_image=None):
 def ingest_resize_gray(img_bgr, size, device=None):
     """datasets/Coco.py:165-179 behind ``cv2.imread``: uint8 [Hs,Ws,3] (numpy or tensor, imread's BGR order) ->
     INTER_AREA resize to ``size`` = (H, W), OpenCV's RGB2GRAY on that memory order, float32 / 255 -> cuda fp32 [H,W].
-    Bit-exact against OpenCV for down-scaling; the uint8 image (3 bytes per source pixel) is what crosses to the GPU."""
+    Bit-exact against OpenCV (down- and up-scaling); the uint8 image (3 bytes per source pixel) is what crosses to the GPU."""
     dev = _dev(device if device is not None else (img_bgr.device if torch.is_tensor(img_bgr) and img_bgr.is_cuda else None))
     x = img_bgr if torch.is_tensor(img_bgr) else torch.from_numpy(np.ascontiguousarray(img_bgr))
     if x.dtype != torch.uint8 or x.dim() != 3 or x.shape[2] != 3:
