@@ -23,9 +23,9 @@ namespace spb {
 // configuration
 // ------------------------------------------------------------------------------------------------
 // OUT_: 0 = ReLU + bf16 NHWC (encoder / head 3x3), 1 = raw fp32 rows staged through shared memory for coalesced
-// stores (convPb: 65 channels), 2 = fp32 rows L2-normalised over the channels (convDb), 3 = softmax probabilities
-// [.,64] fp32 (convPb, dustbin dropped), 4 = the same probabilities written as fp16 planes with the depth-to-space
-// indexing and the valid mask applied (convPb inside the HA pass; consumed by ha_fast.cu).
+// stores (convPb: 65 channels), 2 = fp32 rows L2-normalised over the channels (convDb), 4 = convPb inside the HA pass:
+// softmax probabilities (dustbin dropped) written as fp16 planes with the depth-to-space indexing and the valid mask
+// applied (consumed by ha_fast.cu).
 // NT_: output tiles per accumulator stage.  With streamed weights (128 -> 128) every weight block that arrives in shared
 // memory is used for TWO tiles (8 MMAs instead of 4): the layer was bound by L2 -> SM weight traffic (288 KB per tile).
 template <int CIN_, int NPAD_, int KS_, bool HALO_, bool BRES_, int NA_, int NB_, bool POOL_, int OUT_, int NT_ = 1>
@@ -40,9 +40,7 @@ struct ConvCfg {
   // write it with one TMA tensor store: per-lane 16-byte global stores at a 256/512-byte stride cost one L1
   // wavefront per lane, in the shared-memory pipe the tensor core reads its operands through
   static constexpr bool TMA_OUT = OUT_ == 0 && NPAD_ >= 128;
-  // OUT_ == 3 (softmax probabilities, fp32 [.,64]): each of the 4 epilogue warps stages 32 pixels x 2 halves of
-  // 32 floats (2 x 4 KB, SWIZZLE_128B) and issues two TMA stores
-  static constexpr int OSTAGE_BYTES = TMA_OUT ? 8 * 4096 : (OUT_ == 3 ? 4 * 8192 : 0);
+  static constexpr int OSTAGE_BYTES = TMA_OUT ? 8 * 4096 : 0;
   static constexpr bool HALO = HALO_ && KS_ > 1, BRES = BRES_;
   static constexpr int TAPS = KS * KS, CHUNKS = CIN / 64;
   static constexpr int TH = 16, TW = 8;
@@ -314,9 +312,9 @@ __global__ void __launch_bounds__(C::THREADS, 1) conv_tc_kernel(const __grid_con
         }
         norm = sqrtf(ss);
       }
-      if (C::OUT == 3 || C::OUT == 4) {
-        // convPb in the HA path: 65-way softmax of the cell in registers (each thread holds its whole row),
-        // dustbin dropped, probabilities written as [.,64] fp32 -- utils/utils.py:514-523 fused here.
+      if (C::OUT == 4) {
+        // convPb in the HA path: 65-way softmax of the cell in registers (each thread holds its whole row), dustbin
+        // dropped -- utils/utils.py:514-523 fused here.
         uint32_t w[80];
 #pragma unroll
         for (int b = 0; b < 5; ++b) tc_ld_nowait<16>(taddr + b * 16, *reinterpret_cast<uint32_t(*)[16]>(&w[b * 16]));
@@ -342,7 +340,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) conv_tc_kernel(const __grid_con
           sum += e;
         }
         const float rs = __frcp_rn(sum);
-        if constexpr (C::OUT == 4) {
+        {
           // depth-to-space + mask + fp16 in the store (utils/d2s.py:8-25, export.py:52): row r of the 8x8 cell is
           // 16 bytes of plane row 8y + r; the 8 lanes of a cell row of the tile write 128 contiguous bytes.
           // A pixel of the warped view that lies outside the source image (mask bit 0) is stored as kHeatMasked.
@@ -367,27 +365,6 @@ __global__ void __launch_bounds__(C::THREADS, 1) conv_tc_kernel(const __grid_con
           }
           continue;
         }
-        // stage [pixel][32 floats] x 2 halves (SWIZZLE_128B) and let TMA write the warp's 4 rows x 8 pixels
-        uint8_t* stg = sOut + (warp - 2) * 8192;
-        if (lane == 0) tma_store_wait_read<0>();  // the previous tile's stores have finished reading the tile
-        __syncwarp();
-#pragma unroll
-        for (int h = 0; h < 2; ++h)
-#pragma unroll
-          for (int c4 = 0; c4 < 8; ++c4) {
-            const int j = h * 32 + c4 * 4;
-            *reinterpret_cast<float4*>(stg + h * 4096 + lane * 128 + ((c4 ^ (lane & 7)) * 16)) =
-                make_float4(__uint_as_float(w[j]) * rs, __uint_as_float(w[j + 1]) * rs, __uint_as_float(w[j + 2]) * rs,
-                            __uint_as_float(w[j + 3]) * rs);
-          }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) {
-          tma_store_4d(&tm_out, smem_u32(stg), 0, x0, y0 + 4 * quad, n);
-          tma_store_4d(&tm_out, smem_u32(stg + 4096), 32, x0, y0 + 4 * quad, n);
-          tma_store_commit();
-        }
-        continue;  // (NT == 1: falls out of the tile loop to the stage advance below)
       }
       uint32_t v[2][BW];
       tc_ld_nowait<BW>(taddr + col0, v[0]);
@@ -501,7 +478,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) conv_tc_kernel(const __grid_con
      }  // tiles of the stage
       if (++as == 2) { as = 0; pacc ^= 1; }
     }
-    if ((C::TMA_OUT || C::OUT == 3) && lane == 0) tma_store_wait_all();
+    if (C::TMA_OUT && lane == 0) tma_store_wait_all();
   }
 
   tc_fence_before();
@@ -1184,19 +1161,6 @@ static int launch(const LayerDev& L, const __nv_bfloat16* in, void* out, int B, 
     rc = C::POOL ? encode_act_map(&tm_out, out, B, H / 2, W / 2, L.cout, 4, 2)
                  : encode_act_map(&tm_out, out, B, H, W, L.cout, 8, 4);
     if (rc != SPB_OK) return rc;
-  } else if (C::OUT == 3) {  // fp32 probabilities [B,H,W,64]: box = 32 floats x 8 pixels x 4 rows
-    EncodeTiledFn enc = get_encode();
-    cuuint64_t dims[4] = {64, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-    cuuint64_t strides[3] = {256, (cuuint64_t)W * 256, (cuuint64_t)H * W * 256};
-    cuuint32_t box[4] = {32, 8, 4, 1};
-    cuuint32_t es[4] = {1, 1, 1, 1};
-    const CUresult r = enc(&tm_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, out, dims, strides, box, es,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-      set_error("conv_tc: cuTensorMapEncodeTiled(probabilities) failed with CUresult %d", (int)r);
-      return SPB_ECUDA;
-    }
   } else {
     tm_out = tm_act;
   }
@@ -1209,7 +1173,7 @@ static int launch(const LayerDev& L, const __nv_bfloat16* in, void* out, int B, 
   a.W = W;
   a.cout = L.cout;
   if (L.pool != (C::POOL ? 1 : 0) || L.relu != (C::OUT == 0 ? 1 : 0) || out_mode != C::OUT ||
-      ((C::OUT == 1 || C::OUT == 3 || C::OUT == 4) && L.cout != 65) || (C::OUT == 4 && !aux)) {
+      ((C::OUT == 1 || C::OUT == 4) && L.cout != 65) || (C::OUT == 4 && !aux)) {
     set_error("conv_tc: kernel configuration does not match the layer (pool %d relu %d out_mode %d)", L.pool, L.relu,
               out_mode);
     return SPB_EINVAL;
@@ -1262,7 +1226,6 @@ int conv_tc(const LayerDev& L, const __nv_bfloat16* in, void* out, int B, int H,
   if (L.ks == 3 && L.cin == 128 && L.cout_pad == 256)
     return halo ? SPB_CONV(128, 256, 3, true, false, 2, 4, false, 0) : SPB_CONV(128, 256, 3, false, false, 3, 4, false, 0);
   if (L.ks == 1 && L.cin == 256 && L.cout_pad == 80 && out_mode == 1) return SPB_CONV(256, 80, 1, false, true, 6, 0, false, 1);
-  if (L.ks == 1 && L.cin == 256 && L.cout_pad == 80 && out_mode == 3) return SPB_CONV(256, 80, 1, false, true, 6, 0, false, 3);
   if (L.ks == 1 && L.cin == 256 && L.cout_pad == 80 && out_mode == 4) return SPB_CONV(256, 80, 1, false, true, 6, 0, false, 4);
   if (L.ks == 1 && L.cin == 256 && L.cout_pad == 256 && out_mode == 2) return SPB_CONV(256, 256, 1, false, true, 4, 0, false, 2);
 #undef SPB_CONV

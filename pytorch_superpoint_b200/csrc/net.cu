@@ -76,7 +76,6 @@ struct StageTimer {
   }
 };
 
-// out_mode: 0 bf16 NHWC, 1 fp32 rows, 2 fp32 L2-normalised rows, 3 softmax probabilities [.,64] (convPb)
 __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ semi, float* __restrict__ probs,
                                                            long long rows) {
   const int lane = threadIdx.x & 31;
@@ -101,10 +100,6 @@ static int run_layer(const Net* net, int li, const void* in, void* out, int B, i
                : conv1a_simt(L, static_cast<const float*>(in), static_cast<__nv_bfloat16*>(out), B, H, W, st);
   if (net->impl == SPB_IMPL_TCGEN05)
     return conv_tc(L, static_cast<const __nv_bfloat16*>(in), out, B, H, W, out_mode, st);
-  if (out_mode == 3) {
-    set_error("run_layer: softmax output is produced by forward() in SIMT mode");
-    return SPB_EINVAL;
-  }
   int rc = conv_simt(L, static_cast<const __nv_bfloat16*>(in), out, B, H, W, out_mode != 0, st);
   if (rc == SPB_OK && out_mode == 2) rc = l2norm_rows(static_cast<float*>(out), (long long)B * H * W, L.cout, st);
   return rc;
@@ -134,18 +129,14 @@ static int forward(const Net* net, const float* x, int B, int H, int W, float* s
   RUN(7, w.buf0, w.buf1, H / 8, W / 8, 0);
   RUN(8, w.buf1, w.buf0, H / 8, W / 8, 0);
   if (semi) RUN(9, w.buf0, semi, H / 8, W / 8, 1);
-  if (probs) {
-    if (net->impl == SPB_IMPL_TCGEN05) {
-      RUN(9, w.buf0, probs, H / 8, W / 8, 3);
-    } else {  // validation path: logits (semi) first, then a softmax kernel
-      if (!semi) {
-        set_error("forward: the SIMT validation path needs a semi buffer to produce probabilities");
-        return SPB_EINVAL;
-      }
-      const long long rows = (long long)B * (H / 8) * (W / 8);
-      softmax_rows_kernel<<<min(ceil_div(rows, 8), kNumSMs * 8), 256, 0, st>>>(semi, probs, rows);
-      SPB_CHECK_LAUNCH();
+  if (probs) {  // validation path: logits (semi) first, then a softmax kernel
+    if (!semi) {
+      set_error("forward: fp32 probabilities need a semi buffer (they are the CUDA-core validation path's form)");
+      return SPB_EINVAL;
     }
+    const long long rows = (long long)B * (H / 8) * (W / 8);
+    softmax_rows_kernel<<<min(ceil_div(rows, 8), kNumSMs * 8), 256, 0, st>>>(semi, probs, rows);
+    SPB_CHECK_LAUNCH();
   }
   if (heat16) {
     if (net->impl != SPB_IMPL_TCGEN05 || !bits) {

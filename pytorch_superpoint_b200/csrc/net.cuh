@@ -69,8 +69,8 @@ bool conv1_fused_supports(int H, int W);  // even H, W % 4 == 0 (TMA row pitch)
 int conv1_fused(const LayerDev& L1a, const LayerDev& L1b, const float* x, __nv_bfloat16* out, int V, int H, int W,
                 cudaStream_t st);
 int conv_tc_prepare(LayerDev& L);  // builds the weight tensor map after w_tc is uploaded
-// out_mode: 0 bf16 NHWC, 1 fp32 rows (cout channels), 2 fp32 rows L2-normalised, 3 softmax probabilities
-// (convPb only: fp32 [.,64], dustbin dropped), 4 = convPb in the HA pass: fp16 probability planes
+// out_mode: 0 bf16 NHWC, 1 fp32 rows (cout channels), 2 fp32 rows L2-normalised, 4 = convPb in the HA pass: softmax
+// probabilities (dustbin dropped) as fp16 planes
 // [B, 8H + 2*kHeatPadY, 8W + 2*kHeatPadX] (softmax, dustbin drop, depth-to-space; aux = the valid-mask bits
 // [B,8H,W] of the warped views: masked pixels are stored as kHeatMasked)
 int conv_tc(const LayerDev& L, const __nv_bfloat16* in, void* out, int B, int H, int W, int out_mode, cudaStream_t st,

@@ -325,3 +325,27 @@ def test_ha_ragged_balanced_shards_sum_to_the_full_heatmap(B, H, W, N, world):
             assert torch.allclose(part[b], ref, rtol=1e-5, atol=1e-6)
         total += part
     assert torch.allclose(total, full, rtol=1e-5, atol=1e-5)            # fp32 summation order differs only
+
+
+@pytest.mark.parametrize("B,H,W,N", [(2, 64, 96, 9), (1, 120, 160, 16)])
+def test_ha_fast_pass_vs_bit_exact_validation_pass(B, H, W, N):
+    """The product pass (folded coordinates, fp16 masked planes, tcgen05 convolutions) against the validation pass
+    (SPB_IMPL_SIMT: the bit-exact warp / mask / aggregate kernels around CUDA-core convolutions with the same bf16
+    numerics): the mask-sum planes agree to the folded un-warp's interpolation error, the heat-maps to a fraction of
+    the 1e-2 tolerance."""
+    from pytorch_superpoint_b200 import SuperPointNet_b200, sample_ha_homographies_device
+    n = SuperPointNet_b200()
+    n.load_state_dict(O.synthetic_state_dict("gauss2", seed=2))
+    imgs = torch.rand(B, H, W, device="cuda", generator=torch.Generator("cuda").manual_seed(H))
+    mu, mf = sample_ha_homographies_device(N, B, seed=H)
+    fast = n.ha_heatmap_sums_batch(imgs, mu, mf).clone()
+    try:
+        n.set_impl("simt")
+        exact = n.ha_heatmap_sums_batch(imgs, mu, mf).clone()
+    finally:
+        n.set_impl("tcgen05")
+    assert torch.isfinite(fast).all() and torch.isfinite(exact).all()
+    assert (fast[:, 1] - exact[:, 1]).abs().max().item() < 2e-2          # sum of masks (values up to N)
+    assert (fast[:, 1] - exact[:, 1]).abs().mean().item() < 1e-3
+    heat_f, heat_e = fast[:, 0] / fast[:, 1], exact[:, 0] / exact[:, 1]
+    assert (heat_f - heat_e).abs().max().item() < 2e-3

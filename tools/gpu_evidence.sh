@@ -1,5 +1,5 @@
 #!/bin/bash
-# evidence job: ncu --set full of one launch of every kernel on the path, summarised ON the box (the .ncu-rep files
+# evidence job (bash tools/gpu_evidence.sh under gpurun): ncu --set full of one launch of every kernel on the path, summarised ON the box (the .ncu-rep files
 # stay in /tmp: gpurun_out/ is limited to 64 MiB), + the launch list of a bench step
 mkdir -p gpurun_out/r2k /tmp/ncu
 cd /root/repo
