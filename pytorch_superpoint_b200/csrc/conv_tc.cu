@@ -1072,7 +1072,8 @@ extern "C" int spb_conv1_fused_set_probe(long long* dev_buf) {  // debug: timeli
 long long* conv1_probe_buf() { return g_conv1_dbg; }
 // conv1a fused into conv1b's kernel: 0 two kernels (A/B tests), 1 the fused block; set_fuse1(-1) restores the default.
 // (Three other fused designs were built, measured slower and removed from the library: column-stacked N = 192 and
-// N = 128 + 64 in round 1, weight-stationary tile pairs -- tools/experiments/conv1_ws.cu -- in round 2)
+// N = 128 + 64 in round 1, weight-stationary tile pairs -- tools/experiments/conv1_ws.cu -- and the block on CTA pairs
+// (cta_group::2) -- tools/experiments/conv1_pair.cu -- in round 2)
 constexpr int kFuse1Default = 1;
 static int g_fuse1 = kFuse1Default;
 extern "C" int spb_conv_tc_set_fuse1(int on) {

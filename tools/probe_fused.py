@@ -1,10 +1,12 @@
-"""Timeline probe of conv1_fused_kernel (CTA 0): per-iteration clock64 stamps of the MMA, stage-1 and epilogue roles."""
+"""Timeline probe of conv1_fused_kernel / conv1_pair_kernel (CTA 0): per-iteration clock64 stamps of the MMA, stage-1
+and epilogue roles.   python tools/probe_fused.py [fuse1 mode: 1 single CTA (default), 2 CTA pairs]"""
 import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from pytorch_superpoint_b200 import SuperPointNet_b200, _lib
 from pytorch_superpoint_b200.synthetic import synthetic_state_dict
 L = _lib.lib()
+L.spb_conv_tc_set_fuse1(int(sys.argv[1]) if len(sys.argv) > 1 else 1)
 net = SuperPointNet_b200(); net.load_state_dict(synthetic_state_dict("gauss2", 1))
 x = torch.rand(100, 1, 240, 320, device="cuda")
 net.forward_nhwc(x, want_desc=False); torch.cuda.synchronize()
