@@ -212,6 +212,24 @@ int spb_net_forward(spb_net* net, const float* x, int B, int H, int W, float* se
  * output NHWC bf16 (fp32 for Pb/Db; Db rows L2-normalised), 2x2 max-pool applied where the network has one. */
 int spb_net_layer(spb_net* net, int layer, const void* in, void* out, int B, int H, int W, void* stream);
 
+/* ---- train-mode BatchNorm (opt-in): the as-written reference never calls .eval() (models/model_wrap.py:111,
+ * Val_model_heatmap.py:61-73), so its conv -> BN -> ReLU blocks (models/unet_parts.py:14-21,
+ * SuperPointNet_gauss2.py:56-69) use the statistics of the current batch.  The host walks the layers with the RAW
+ * conv weights (no folded BN), everything in fp32: convolution -> batch statistics -> normalise + ReLU + pool.
+ * spb_conv_f32: "same" convolution on CUDA cores, in NHWC fp32 [B,H,W,cin], w fp32 [ks*ks][cin][cout_pad] (zero
+ *   padded), bias [cout_pad], out fp32 rows [B*H*W, cout]; (ks, cout_pad) in 3x3: 64 / 128 / 256, 1x1: 80 / 256.
+ * spb_bn_batch_stats: rows [R,C] -> mean, BIASED variance (F.batch_norm(training=True)) and scale = gamma /
+ *   sqrt(var + eps), shift = beta - mean * scale (gamma / beta NULL: 1 / 0; mean / var may be NULL); C <= 256.
+ * spb_bn_apply: y = x * scale[c] + shift[c], optional ReLU, optional 2x2 max-pool; out = bf16 NHWC (out_f32 == 0) or
+ *   fp32 rows; l2norm != 0: channel L2 normalisation of the fp32 rows (the descriptor head). */
+int spb_conv_f32(const float* in, const float* w, const float* bias, float* out, int B, int H, int W, int cin, int cout,
+                 int cout_pad, int ks, void* stream);
+size_t spb_bn_batch_stats_workspace_bytes(int C);
+int spb_bn_batch_stats(const float* rows, long long R, int C, const float* gamma, const float* beta, float eps,
+                       float* mean, float* var, float* scale, float* shift, void* ws, size_t ws_bytes, void* stream);
+int spb_bn_apply(const float* rows, int B, int H, int W, int C, const float* scale, const float* shift, int relu,
+                 int pool, void* out, int out_f32, int l2norm, void* stream);
+
 /* ---- the whole HA step for one image (datasets/Coco.py:262-284 + export.py:309-310) -------------
  * img [H,W] fp32; mats_fwd = sample['inv_homographies'] (warps the image, defines the valid mask),
  * mats_unwarp = sample['homographies'] (un-warps the heat-map); both [N,3,3] for the N views THIS

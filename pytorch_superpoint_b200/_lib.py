@@ -59,6 +59,10 @@ PROTOTYPES = {
     "spb_net_workspace_bytes": (_z, [_i, _i, _i, _i]),
     "spb_net_forward": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _z, _p]),
     "spb_net_layer": (_i, [_p, _i, _p, _p, _i, _i, _i, _p]),
+    "spb_conv_f32": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "spb_bn_batch_stats_workspace_bytes": (_z, [_i]),
+    "spb_bn_batch_stats": (_i, [_p, _ll, _i, _p, _p, _f, _p, _p, _p, _p, _p, _z, _p]),
+    "spb_bn_apply": (_i, [_p, _i, _i, _i, _i, _p, _p, _i, _i, _p, _i, _i, _p]),
     "spb_ha_workspace_bytes": (_z, [_i, _i, _i]),
     "spb_ha_heatmap_sums": (_i, [_p, _p, _p, _p, _i, _i, _i, _p, _i, _p, _z, _p]),
     "spb_ha_workspace_bytes_batch": (_z, [_p, _i, _i, _i, _i]),

@@ -82,6 +82,13 @@ class HAExporter:
         key = (B, N, H, W, bool(shared), rank, world, cap)
         if key not in self._plans:
             plan = plan_batch(B, N, rank, world, cap)
+            if getattr(self.net, "bn_mode", "eval") == "batch" and (world > 1 or any(p.accumulate for p in plan.passes)):
+                # batch statistics = the statistics of ALL views of an image (the reference's batch): they cannot be
+                # split over ranks or passes without changing the result
+                raise NotImplementedError(
+                    "bn_mode='batch' needs all homographies of an image in one pass on one GPU "
+                    f"(got world={world}, {N} views, {cap} views per pass): use HAExporter(sharded=False) and give "
+                    "every rank its own images")
             dev_passes = []
             for p in plan.passes:
                 vm = p.view_mat % N if shared else p.view_mat
@@ -237,7 +244,8 @@ def export_detector_homoAdapt_b200(config, output_dir, args=None, loader=None, n
     if net is None:
         path = config["pretrained"]
         ckpt = torch.load(path, map_location=lambda storage, loc: storage)
-        net = SuperPointNet_b200()
+        # model.b200_bn_mode: 'eval' (default, the product path) or 'batch' (the as-written train-mode statistics)
+        net = SuperPointNet_b200(bn_mode=config["model"].get("b200_bn_mode", "eval"))
         net.load_state_dict(ckpt["model_state_dict"] if path[-4:] == ".tar" else ckpt)
     sub = config["model"].get("subpixel", {}) or {}
     subpixel = bool(sub.get("enable", False))

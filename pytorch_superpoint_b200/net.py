@@ -3,9 +3,10 @@
 Same constructor / ``forward`` / ``load_state_dict`` surface as ``models/SuperPointNet_gauss2.py:11-70``
 (and ``models/SuperPointNet.py``, ``models/SuperPointNet_pretrained.py``): ``forward(x[B,1,H,W])`` returns
 ``{'semi': [B,65,H/8,W/8], 'desc': [B,256,H/8,W/8]}``.  Any of the three reference state-dict layouts is
-accepted; BatchNorm runs in eval mode (running statistics), folded into the conv weights -- see DESIGN.md
-for why the as-written train-mode statistics are not reproduced.  The math runs in libspb200.so
-(bf16 tcgen05 implicit-GEMM); PyTorch only owns the buffers.
+accepted; BatchNorm runs in eval mode (running statistics), folded into the conv weights -- the product path,
+see DESIGN.md.  ``bn_mode='batch'`` is the opt-in compatibility path for the as-written reference, which never
+calls ``.eval()`` (models/model_wrap.py:111): every BN then uses the statistics of the current batch (CUDA-core
+kernels + three passes per layer, ``csrc/bn.cu``).  The math runs in libspb200.so; PyTorch only owns the buffers.
 """
 from __future__ import annotations
 
@@ -45,11 +46,10 @@ def _norm_device(device=None) -> torch.device:
     return d if d.index is not None else torch.device("cuda", torch.cuda.current_device())
 
 
-def fold_state_dict(state_dict, eps: float = 1e-5):
-    """Any reference layout -> 12 (weight OIHW fp32, bias fp32) numpy pairs with eval-mode BN folded in."""
+def _layer_params(state_dict):
+    """Any reference layout -> per layer (weight OIHW, bias, (gamma, beta, running_mean, running_var) or None), float64."""
     sd = {(k[7:] if k.startswith("module.") else k): v for k, v in state_dict.items()}
     gauss2 = "inc.conv.conv.0.weight" in sd
-    ws, bs = [], []
     for name, (cin, cout, ks) in zip(LAYER_NAMES, LAYER_SHAPES):
         cname, bname = _GAUSS2[name] if gauss2 else (name, "bn" + name[4:])
         if cname + ".weight" not in sd:
@@ -58,25 +58,55 @@ def fold_state_dict(state_dict, eps: float = 1e-5):
         b = sd[cname + ".bias"].detach().to("cpu", torch.float64)
         if tuple(w.shape) != (cout, cin, ks, ks):
             raise ValueError(f"{cname}.weight has shape {tuple(w.shape)}, expected {(cout, cin, ks, ks)}")
+        bn = None
         if bname + ".running_mean" in sd:
-            g, beta, m, v = (sd[bname + s].detach().to("cpu", torch.float64)
-                             for s in (".weight", ".bias", ".running_mean", ".running_var"))
+            bn = tuple(sd[bname + s].detach().to("cpu", torch.float64)
+                       for s in (".weight", ".bias", ".running_mean", ".running_var"))
+        yield w, b, bn
+
+
+def _as_np(t):
+    return np.ascontiguousarray(t.to(torch.float32).numpy())
+
+
+def fold_state_dict(state_dict, eps: float = 1e-5):
+    """Any reference layout -> 12 (weight OIHW fp32, bias fp32) numpy pairs with eval-mode BN folded in."""
+    ws, bs = [], []
+    for w, b, bn in _layer_params(state_dict):
+        if bn is not None:
+            g, beta, m, v = bn
             s = g / torch.sqrt(v + eps)
             w = w * s[:, None, None, None]
             b = (b - m) * s + beta
-        ws.append(np.ascontiguousarray(w.to(torch.float32).numpy()))
-        bs.append(np.ascontiguousarray(b.to(torch.float32).numpy()))
+        ws.append(_as_np(w))
+        bs.append(_as_np(b))
     return ws, bs
+
+
+def raw_state_dict(state_dict):
+    """Any reference layout -> 12 RAW (weight, bias) numpy pairs and the per-layer BN affine ``(gamma, beta)`` (or
+    None for a layer without BN): what the train-mode (batch statistics) path needs."""
+    ws, bs, affine = [], [], []
+    for w, b, bn in _layer_params(state_dict):
+        ws.append(_as_np(w))
+        bs.append(_as_np(b))
+        affine.append(None if bn is None else (bn[0].to(torch.float32), bn[1].to(torch.float32)))
+    return ws, bs, affine
 
 
 class SuperPointNet_b200(nn.Module):
     """B200-native SuperPoint network.  ``SuperPointNet_b200(subpixel_channel=1)`` like the reference."""
 
-    def __init__(self, subpixel_channel=1, impl: str = "tcgen05"):
+    def __init__(self, subpixel_channel=1, impl: str = "tcgen05", bn_mode: str = "eval"):
         super().__init__()
+        if bn_mode not in ("eval", "batch"):
+            raise ValueError(f"bn_mode must be 'eval' or 'batch', got {bn_mode!r}")
+        self.bn_mode = bn_mode
+        self.bn_eps = 1e-5  # nn.BatchNorm2d default, what every reference network uses
         self._sd = collections.OrderedDict()
         self._handle = None
         self._handle_dev = None
+        self._raw = None  # bn_mode='batch': fp32 raw conv weights + BN affine parameters on the device
         self._ws = None
         self._impl = impl
         self._ha_overlap = False  # C-handle settings live here and are re-applied whenever the handle is rebuilt
@@ -109,6 +139,7 @@ class SuperPointNet_b200(nn.Module):
         if self._handle is not None:
             _lib.lib().spb_net_destroy(self._handle)
         self._handle = None
+        self._raw = None
         self._ws = None
 
     def __del__(self):
@@ -165,6 +196,8 @@ class SuperPointNet_b200(nn.Module):
         if ch != 1 or H % 8 or W % 8:
             raise ValueError(f"expected [B,1,H,W] with H, W multiples of 8, got {tuple(x.shape)}")
         dev = x.device
+        if self.bn_mode == "batch":
+            return self._forward_batch_bn(x.reshape(B, H, W), want_desc)
         h = self.handle(dev)
         L = _lib.lib()
         semi = torch.empty((B, H // 8, W // 8, 65), device=dev, dtype=torch.float32)
@@ -176,6 +209,80 @@ class SuperPointNet_b200(nn.Module):
                                          desc.data_ptr() if want_desc else None, ws.data_ptr(), ws.numel(),
                                          torch.cuda.current_stream().cuda_stream), "net_forward")
         return semi, desc
+
+    # ---- train-mode BatchNorm (batch statistics): the as-written reference, opt-in ------------------------
+    def _raw_weights(self, dev):
+        """fp32 device copies of the RAW conv weights as [tap][cin][cout_pad] (+ bias [cout_pad]) and the BN affine
+        parameters of every layer: what spb_conv_f32 / spb_bn_batch_stats read."""
+        dev = _norm_device(dev)
+        if self._raw is None or self._raw["dev"] != dev:
+            ws, bs, affine = raw_state_dict(self._sd)
+            layers = []
+            for (cin, cout, ks), w, b, a in zip(LAYER_SHAPES, ws, bs, affine):
+                cpad = -(-cout // 16) * 16
+                wt = torch.zeros((ks * ks, cin, cpad), dtype=torch.float32)
+                wt[:, :, :cout] = torch.from_numpy(w).permute(2, 3, 1, 0).reshape(ks * ks, cin, cout)
+                bt = torch.zeros(cpad, dtype=torch.float32)
+                bt[:cout] = torch.from_numpy(b)
+                layers.append(dict(w=wt.to(dev), b=bt.to(dev), cpad=cpad,
+                                   affine=None if a is None else (a[0].to(dev).contiguous(), a[1].to(dev).contiguous())))
+            self._raw = dict(dev=dev, layers=layers)
+        return self._raw
+
+    def _forward_batch_bn(self, x: torch.Tensor, want_desc: bool):
+        """x [B,H,W] cuda fp32 -> (semi, desc) NHWC fp32 like forward_nhwc, every BatchNorm normalising with the
+        statistics of THIS batch (F.batch_norm(training=True): biased variance), as models/unet_parts.py:14-21 /
+        SuperPointNet_gauss2.py:56-69 do when the module is left in train mode.  Per layer, all fp32: convolution ->
+        per-channel statistics -> scale / shift -> normalise + ReLU + 2x2 max-pool (csrc/bn.cu)."""
+        dev = x.device
+        raw = self._raw_weights(dev)
+        L = _lib.lib()
+        B, H, W = x.shape
+        st = torch.cuda.current_stream().cuda_stream
+        f32 = dict(device=dev, dtype=torch.float32)
+        ws = torch.empty(L.spb_bn_batch_stats_workspace_bytes(256), device=dev, dtype=torch.uint8)
+
+        def block(li, inp, hh, ww, relu, pool, l2norm=False):
+            cin, cout, ks = LAYER_SHAPES[li]
+            lay = raw["layers"][li]
+            rows = torch.empty((B * hh * ww, cout), **f32)
+            _lib.check(L.spb_conv_f32(inp.data_ptr(), lay["w"].data_ptr(), lay["b"].data_ptr(), rows.data_ptr(), B, hh, ww,
+                                      cin, cout, lay["cpad"], ks, st), "conv_f32")
+            scale, shift = torch.empty(cout, **f32), torch.empty(cout, **f32)
+            if lay["affine"] is None:  # a network without BN (superpoint_v1 layout): identity transform
+                scale.fill_(1.0)
+                shift.zero_()
+            else:
+                g, beta = lay["affine"]
+                _lib.check(L.spb_bn_batch_stats(rows.data_ptr(), rows.shape[0], cout, g.data_ptr(), beta.data_ptr(),
+                                                self.bn_eps, None, None, scale.data_ptr(), shift.data_ptr(),
+                                                ws.data_ptr(), ws.numel(), st), "bn_batch_stats")
+            oh, ow = (hh // 2, ww // 2) if pool else (hh, ww)
+            out = torch.empty((B, oh, ow, cout), **f32)
+            _lib.check(L.spb_bn_apply(rows.data_ptr(), B, hh, ww, cout, scale.data_ptr(), shift.data_ptr(), int(relu),
+                                      int(pool), out.data_ptr(), 1, int(l2norm), st), "bn_apply")
+            return out, oh, ow
+
+        with torch.cuda.device(dev):
+            t, hh, ww = x.contiguous(), H, W  # [B,H,W] = NHWC with one channel
+            for li in range(8):
+                t, hh, ww = block(li, t, hh, ww, True, li in (1, 3, 5))
+            pa, _, _ = block(8, t, hh, ww, True, False)
+            semi, _, _ = block(9, pa, hh, ww, False, False)
+            desc = None
+            if want_desc:
+                da, _, _ = block(10, t, hh, ww, True, False)
+                desc, _, _ = block(11, da, hh, ww, False, False, l2norm=True)
+        return semi, desc
+
+    def _ha_sums_batch_bn(self, img, mu, mf, sums, accumulate):
+        """One image, ALL of its views in one batch (their statistics are the BN statistics): the reference's own
+        warp (spb_inv_warp_image_batch) -> batch-statistics network -> fused aggregate."""
+        from . import ops
+        H, W = img.shape
+        views = ops.inv_warp_image_batch(img, mf)  # [N,1,H,W]
+        semi, _ = self.forward_nhwc(views, want_desc=False)
+        return ops.ha_aggregate(semi, mu, mf, H, W, sums=sums, accumulate=accumulate)
 
     def forward(self, x):
         semi, desc = self.forward_nhwc(x, want_desc=True)
@@ -225,6 +332,20 @@ class SuperPointNet_b200(nn.Module):
         vm = None if view_mat is None else view_mat.to(dev, torch.int32).contiguous()
         if vo.numel() != B + 1 or (vm is None and mu.reshape(-1, 3, 3).shape[0] != V) or (vm is not None and vm.numel() != V):
             raise ValueError("view_image / view_mat must be [V] and view_offsets [B+1]")
+        if self.bn_mode == "batch":
+            # the caller guarantees that the pass holds EVERY view of each of its images (HAExporter checks its plan)
+            if sums is None:
+                sums = torch.empty((B, 2, H, W), device=dev, dtype=torch.float32)
+                accumulate = False
+            off = vo.cpu().tolist()
+            mu3, mf3 = mu.reshape(-1, 3, 3), mf.reshape(-1, 3, 3)
+            for b in range(B):
+                idx = torch.arange(off[b], off[b + 1], device=dev) if vm is None else vm[off[b]:off[b + 1]].long()
+                if idx.numel():
+                    self._ha_sums_batch_bn(imgs[b], mu3[idx], mf3[idx], sums[b], accumulate)
+                elif not accumulate:
+                    sums[b].zero_()
+            return sums
         h = self.handle(dev)
         L = _lib.lib()
         nbytes = L.spb_ha_workspace_bytes_ragged(B, V, int(max_views), H, W)
@@ -259,6 +380,13 @@ class SuperPointNet_b200(nn.Module):
         N = mu.shape[-3]
         if not shared and mu.shape[0] != B:
             raise ValueError("per-image homographies must be [B,N,3,3]")
+        if self.bn_mode == "batch":  # per image, all N views at once (chunk is ignored: the statistics need them all)
+            if sums is None:
+                sums = torch.empty((B, 2, H, W), device=dev, dtype=torch.float32)
+                accumulate = False
+            for b in range(B):
+                self._ha_sums_batch_bn(imgs[b], mu if shared else mu[b], mf if shared else mf[b], sums[b], accumulate)
+            return sums
         h = self.handle(dev)
         L = _lib.lib()
         _lib.check(L.spb_net_set_ha_chunk(h, int(chunk)), "set_ha_chunk")

@@ -64,7 +64,8 @@ class Val_model_heatmap_b200(SuperPointFrontend_b200):
     # Val_model_heatmap.py:61-73: '*.tar' checkpoints carry {'model_state_dict': ...}
     def loadModel(self):
         ckpt = torch.load(self.weights_path, map_location=lambda storage, loc: storage)
-        self.net = SuperPointNet_b200(**{k: v for k, v in (self.params or {}).items() if k == "subpixel_channel"})
+        self.net = SuperPointNet_b200(**{k: v for k, v in (self.params or {}).items() if k == "subpixel_channel"},
+                                      bn_mode=self.config.get("b200_bn_mode", "eval"))
         self.net.load_state_dict(ckpt["model_state_dict"])
 
     # Val_model_heatmap.py:88-111

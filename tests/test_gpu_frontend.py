@@ -119,6 +119,44 @@ def test_export_entry_writes_reference_npz(tmp_path):
     assert export_detector_homoAdapt_b200(cfg, str(tmp_path), loader=samples, net=net) == 0
 
 
+def test_export_entry_train_mode_bn_from_config(tmp_path):
+    """``model.b200_bn_mode: 'batch'`` in the YAML of the export entry: the checkpoint is loaded into the train-mode
+    BatchNorm path (what the reference's export actually runs, model_wrap.py:111) and the written points are the
+    oracle's run with bn_mode='batch' -- heat-map within 1e-3, the same key-point set."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from pytorch_superpoint_b200 import make_ha_homographies
+    from pytorch_superpoint_b200.export import export_detector_homoAdapt_b200
+    sd = O.synthetic_state_dict("gauss2", seed=4)
+    ckpt = os.path.join(str(tmp_path), "ckpt.pth.tar")
+    torch.save({"model_state_dict": sd}, ckpt)
+    H, W, N = 64, 96, 16
+    rng = np.random.RandomState(5)
+    img = np.clip(0.4 + 0.05 * rng.randn(H, W), 0, 1).astype(np.float32)
+    for _ in range(8):
+        x0, y0 = rng.randint(0, W - 10), rng.randint(0, H - 10)
+        img[y0:y0 + rng.randint(5, 20), x0:x0 + rng.randint(5, 30)] = rng.uniform(0, 1)
+    mu, mf = make_ha_homographies(N, seed=9)
+    samples = [{"image_2D": torch.from_numpy(img)[None, None], "name": ["a"], "homographies": torch.from_numpy(mu)[None],
+                "inv_homographies": torch.from_numpy(mf)[None]}]
+    cfg = {"model": {"nms": 4, "top_k": 100, "detection_threshold": 0.015, "subpixel": {"enable": False},
+                     "b200_bn_mode": "batch"},
+           "pretrained": ckpt,
+           "data": {"export_folder": "train", "dataset": "Coco",
+                    "homography_adaptation": {"num": N, "homographies": {"params": {}}}}}
+    assert export_detector_homoAdapt_b200(cfg, str(tmp_path), loader=samples) == 1
+    pts = np.load(os.path.join(str(tmp_path), "predictions", "train", "a.npz"))["pts"]
+    ref, ref_heat = O.ha_export_one(img, mu, mf, O.canonical_params(sd), top_k=100, bn_mode="batch", return_heat=True)
+    ref_eval = O.ha_export_one(img, mu, mf, O.canonical_params(sd), top_k=100, bn_mode="eval")
+    a, b = set(map(tuple, pts[:, :2])), set(map(tuple, ref[:, :2]))
+    assert len(a & b) >= 0.97 * len(a | b)
+    common = sorted(a & b)
+    conf = {tuple(p[:2]): p[2] for p in pts}
+    conf_ref = {tuple(p[:2]): p[2] for p in ref}
+    assert max(abs(conf[k] - conf_ref[k]) for k in common) < 1e-3
+    assert len(a & set(map(tuple, ref_eval[:, :2]))) < len(a & b)  # not the eval-mode answer
+
+
 def test_export_headline_config_vs_oracle():
     """The BASELINE configuration itself: one 240x320 image, 100 homographies, through HAExporter.export_batch
     against the CPU oracle's ha_export_one -- aggregated heat-map within 1e-2, the mask-sum plane within fp32

@@ -349,3 +349,148 @@ def test_ha_fast_pass_vs_bit_exact_validation_pass(B, H, W, N):
     assert (fast[:, 1] - exact[:, 1]).abs().mean().item() < 1e-3
     heat_f, heat_e = fast[:, 0] / fast[:, 1], exact[:, 0] / exact[:, 1]
     assert (heat_f - heat_e).abs().max().item() < 2e-3
+
+
+# ---- train-mode BatchNorm (bn_mode='batch'): the as-written reference never calls .eval() --------------------------
+@pytest.mark.parametrize("R,C", [(1000, 64), (777, 65), (4096, 128), (50, 256), (3, 64)])
+def test_bn_batch_stats_vs_torch(R, C):
+    """spb_bn_batch_stats: mean / BIASED variance / scale / shift of fp32 rows vs a float64 torch computation."""
+    from pytorch_superpoint_b200 import _lib
+    L = _lib.lib()
+    g = torch.Generator("cuda").manual_seed(R + C)
+    rows = torch.randn(R, C, device="cuda", generator=g) * 3 + torch.arange(C, device="cuda") * 0.1
+    gamma, beta = torch.rand(C, device="cuda", generator=g) + 0.5, torch.randn(C, device="cuda", generator=g)
+    mean, var, scale, shift = (torch.empty(C, device="cuda") for _ in range(4))
+    ws = torch.empty(L.spb_bn_batch_stats_workspace_bytes(C), dtype=torch.uint8, device="cuda")
+    _lib.check(L.spb_bn_batch_stats(rows.data_ptr(), R, C, gamma.data_ptr(), beta.data_ptr(), 1e-5, mean.data_ptr(),
+                                    var.data_ptr(), scale.data_ptr(), shift.data_ptr(), ws.data_ptr(), ws.numel(),
+                                    torch.cuda.current_stream().cuda_stream), "bn_batch_stats")
+    r64 = rows.double()
+    m, v = r64.mean(0), r64.var(0, unbiased=False)
+    sc = gamma.double() / torch.sqrt(v + 1e-5)
+    assert torch.allclose(mean.double(), m, rtol=1e-6, atol=1e-6) and torch.allclose(var.double(), v, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(scale.double(), sc, rtol=1e-5) and torch.allclose(shift.double(), beta.double() - m * sc, rtol=1e-5, atol=1e-5)
+    # the transform reproduces F.batch_norm(training=True)
+    y = torch.nn.functional.batch_norm(rows.t()[None], None, None, gamma, beta, training=True, eps=1e-5)[0].t()
+    assert (rows * scale + shift - y).abs().max().item() < 1e-4
+
+
+@pytest.mark.parametrize("B,H,W,cin,cout,ks", [(2, 16, 24, 1, 64, 3), (2, 9, 13, 64, 64, 3), (1, 8, 8, 64, 128, 3),
+                                                (3, 6, 10, 128, 128, 3), (1, 5, 7, 128, 256, 3), (2, 4, 6, 256, 65, 1),
+                                                (2, 4, 6, 256, 256, 1)])
+def test_conv_f32_vs_torch(B, H, W, cin, cout, ks):
+    """spb_conv_f32 (the convolution of the train-mode BN path) vs torch's fp32 conv2d on the same operands."""
+    from pytorch_superpoint_b200 import _lib
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(cin + cout + H)
+    x = torch.randn(B, cin, H, W, generator=g)
+    w = torch.randn(cout, cin, ks, ks, generator=g) * (2.0 / (cin * ks * ks)) ** 0.5
+    b = torch.randn(cout, generator=g)
+    cpad = -(-cout // 16) * 16
+    wt = torch.zeros(ks * ks, cin, cpad)
+    wt[:, :, :cout] = w.permute(2, 3, 1, 0).reshape(ks * ks, cin, cout)
+    bt = torch.zeros(cpad)
+    bt[:cout] = b
+    xin = x.permute(0, 2, 3, 1).contiguous().cuda()
+    out = torch.full((B, H, W, cout), float("nan"), device="cuda")
+    wt, bt = wt.cuda(), bt.cuda()
+    _lib.check(L.spb_conv_f32(xin.data_ptr(), wt.data_ptr(), bt.data_ptr(), out.data_ptr(), B, H, W, cin, cout, cpad, ks,
+                              torch.cuda.current_stream().cuda_stream), "conv_f32")
+    torch.backends.cudnn.allow_tf32 = False
+    ref = torch.nn.functional.conv2d(x.double(), w.double(), b.double(), padding=ks // 2).permute(0, 2, 3, 1)
+    assert (out.cpu().double() - ref).abs().max().item() < 1e-4 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("B,H,W,C,relu,pool,f32", [(2, 8, 12, 64, 1, 1, 0), (3, 6, 10, 128, 1, 0, 0), (1, 4, 6, 65, 0, 0, 1),
+                                                    (2, 4, 4, 256, 0, 0, 1), (1, 16, 8, 64, 1, 1, 1)])
+def test_bn_apply_vs_torch(B, H, W, C, relu, pool, f32):
+    from pytorch_superpoint_b200 import _lib
+    L = _lib.lib()
+    g = torch.Generator("cuda").manual_seed(B * H + C)
+    rows = torch.randn(B, H, W, C, device="cuda", generator=g)
+    scale, shift = torch.rand(C, device="cuda", generator=g) + 0.5, torch.randn(C, device="cuda", generator=g)
+    oh, ow = (H // 2, W // 2) if pool else (H, W)
+    l2 = int(bool(f32) and C == 256)
+    out = torch.empty((B, oh, ow, C), device="cuda", dtype=torch.float32 if f32 else torch.bfloat16)
+    _lib.check(L.spb_bn_apply(rows.data_ptr(), B, H, W, C, scale.data_ptr(), shift.data_ptr(), relu, pool, out.data_ptr(),
+                              f32, l2, torch.cuda.current_stream().cuda_stream), "bn_apply")
+    y = rows * scale + shift
+    if pool:
+        y = torch.nn.functional.max_pool2d(y.permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1)
+    if relu:
+        y = torch.relu(y)
+    if l2:
+        y = y / y.norm(dim=-1, keepdim=True)
+    if f32:
+        assert (out - y).abs().max().item() < 1e-5
+    else:
+        assert torch.equal(out, y.to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("layout", ["gauss2", "bnflat", "v1"])
+def test_forward_batch_bn_vs_reference_golden(layout, golden):
+    """bn_mode='batch' on the reference's golden input: the unmodified reference network left in TRAIN mode (what
+    export.py actually runs, model_wrap.py:111) -- semi / desc within the bf16 tolerance; and the two BN modes
+    really differ on this input (so the test cannot pass by running eval mode)."""
+    from pytorch_superpoint_b200 import SuperPointNet_b200, flattenDetection
+    g = golden("net")
+    key = "eval" if layout == "v1" else "batch"  # the BN-free network has only one mode
+    n = SuperPointNet_b200(bn_mode="batch")
+    n.load_state_dict(O.synthetic_state_dict(layout, seed=1))
+    out = n(torch.from_numpy(g["x"]).cuda())
+    semi, desc = out["semi"], out["desc"]
+    ref_semi = torch.from_numpy(g[f"{layout}_{key}_semi"]).cuda()
+    ref_desc = torch.from_numpy(g[f"{layout}_{key}_desc"]).cuda()
+    assert tuple(semi.shape) == tuple(ref_semi.shape) and tuple(desc.shape) == tuple(ref_desc.shape)
+    heat, ref_heat = flattenDetection(semi.contiguous(), True), flattenDetection(ref_semi, True)
+    assert (heat - ref_heat).abs().max().item() < 1e-4          # fp32 end to end: far inside the bf16 tolerance
+    assert (semi - ref_semi).abs().max().item() < 2e-3
+    assert (desc * ref_desc).sum(1).min().item() > 0.99999
+    assert (desc.norm(dim=1) - 1).abs().max().item() < 1e-4
+    if layout != "v1":
+        other = torch.from_numpy(g[f"{layout}_eval_semi"]).cuda()
+        assert (other - ref_semi).abs().max().item() > 10 * (semi - ref_semi).abs().max().item()
+
+
+def test_forward_batch_bn_vs_oracle_larger_batch():
+    """100 views of 64x96 (the export's batch: all views of one image): batch-statistics network vs the fp32 oracle."""
+    from pytorch_superpoint_b200 import SuperPointNet_b200, flattenDetection
+    sd = O.synthetic_state_dict("gauss2", seed=5)
+    x = torch.rand(100, 1, 64, 96, generator=torch.Generator().manual_seed(3))
+    n = SuperPointNet_b200(bn_mode="batch")
+    n.load_state_dict(sd)
+    semi, desc = n.forward_nhwc(x.cuda())
+    ref_semi, ref_desc = O.net_forward(O.canonical_params(sd), x, bn_mode="batch")
+    heat = flattenDetection(semi.permute(0, 3, 1, 2).contiguous(), True).cpu()
+    ref_heat = flattenDetection(ref_semi.cuda(), True).cpu()
+    assert (heat - ref_heat).abs().max().item() < 1e-4
+    assert (desc.permute(0, 3, 1, 2).cpu() * ref_desc).sum(1).min().item() > 0.99999
+
+
+def test_ha_export_batch_bn_vs_oracle():
+    """Whole HA export of one image with train-mode BN (the as-written reference): aggregated heat-map vs the fp32
+    oracle run with bn_mode='batch'; a plan that would split an image's views is refused, not silently changed."""
+    from pytorch_superpoint_b200 import SuperPointNet_b200, make_ha_homographies
+    from pytorch_superpoint_b200.export import HAExporter
+    H, W, N = 64, 96, 24
+    rng = np.random.RandomState(11)
+    img = np.clip(0.4 + 0.05 * rng.randn(H, W), 0, 1).astype(np.float32)
+    for _ in range(10):
+        x0, y0 = rng.randint(0, W - 10), rng.randint(0, H - 10)
+        img[y0:y0 + rng.randint(5, 20), x0:x0 + rng.randint(5, 30)] = rng.uniform(0, 1)
+    mu, mf = make_ha_homographies(N, seed=4)
+    sd = O.synthetic_state_dict("gauss2", seed=6)
+    n = SuperPointNet_b200(bn_mode="batch")
+    n.load_state_dict(sd)
+    ex = HAExporter(n, conf_thresh=0.015, nms_dist=4, top_k=600)
+    ti, tu, tf = torch.from_numpy(img), torch.from_numpy(mu), torch.from_numpy(mf)
+    pts = ex.export_image(ti, tu, tf)
+    heat = ex.last_heat(1, H, W)[0].cpu().numpy()
+    ref_pts, ref_heat = O.ha_export_one(img, mu, mf, O.canonical_params(sd), bn_mode="batch", return_heat=True)
+    _, eval_heat = O.ha_export_one(img, mu, mf, O.canonical_params(sd), bn_mode="eval", return_heat=True)
+    err = np.abs(heat - ref_heat).max()
+    assert err < 1e-3 and np.abs(eval_heat - ref_heat).max() > 5 * err
+    assert np.array_equal(pts[:, :2], ref_pts[:, :2]) or len(set(map(tuple, pts[:, :2])) & set(map(tuple, ref_pts[:, :2]))) >= 0.98 * len(ref_pts)
+    assert pts.shape[1] == 3 and pts.dtype == np.float64
+    with pytest.raises(NotImplementedError):
+        HAExporter(n, chunk=8).export_image(ti, tu, tf)
