@@ -116,6 +116,8 @@ def ha_warp_views(imgs, mats_fwd, view_image=None):
     if x.dim() == 2:
         x = x[None]
     nb, H, W = x.shape
+    if H < 8 or W < 8 or W % 8:
+        raise ValueError(f"ha_warp_views: needs H >= 8 and W a multiple of 8 (packed mask bytes), got {H}x{W}")
     m = _cu(mats_fwd, dev).reshape(-1, 3, 3)
     V = m.shape[0]
     if view_image is None:
