@@ -21,7 +21,10 @@ when the homographies are sharded over ranks) -> divide -> threshold + greedy NM
   roofline   the dominant kernel (conv1_fused_kernel: conv1a+conv1b+pool, 44 % of the conv FLOPs) against the
              measured bf16 tensor peak (sustained when the clock record shows the power cap, burst otherwise)
   cpu_baseline  the reference's own CPU path on this box's host cores (rank 0, N=1 only): the UNMODIFIED reference
-             functions from baseline/_ref when that copy travelled (kind "reference"), else the oracle port
+             functions from baseline/_ref when that copy travelled (kind "reference"), else the oracle port; with the
+             wall time of every stage (stages_ms)
+  train_mode_bn (c2, N=1) the as-written reference (BN layers left in train mode) on the host cores next to
+             SuperPointNet_b200(bn_mode='batch'), one image each, with the key-point overlap of the two (informational)
   shard_check (N>1) a few images recomputed unsharded on rank 0 outside the timed region vs the sharded result
   --impl reference   times that CPU arm as the main line (one full image, all 100 homographies, per step)
 """
@@ -190,21 +193,38 @@ class CpuArm:
         self.kind = "reference" if self.ref is not None else "port"
         self.params = None if self.ref is not None else O.canonical_params(self.sd)
 
-    def ha_image(self, img, mu, mf):
-        """img [H,W] numpy, mu / mf [N,3,3] numpy -> float64 [K,3] key-points (export.py:283-328 for one image)."""
+    def ha_image(self, img, mu, mf, train_bn=False):
+        """img [H,W] numpy, mu / mf [N,3,3] numpy -> float64 [K,3] key-points (export.py:283-328 for one image).
+        ``train_bn``: leave the network in train mode = the as-written reference (model_wrap.py:111 never calls
+        .eval()), batch statistics over the N views.  ``self.stages`` receives the wall time of every stage in ms."""
         wl = self.wl
         if self.ref is None:
-            return self.O.ha_export_one(img, mu, mf, self.params, THR, NMS, wl["topk"])
+            t0 = time.perf_counter()
+            pts = self.O.ha_export_one(img, mu, mf, self.params, THR, NMS, wl["topk"], bn_mode="batch" if train_bn else "eval")
+            self.stages = {"all": round((time.perf_counter() - t0) * 1e3, 1)}
+            return pts
         ref, fe = self.ref, self.fe
         H, W = img.shape
         x = torch.from_numpy(img)[None, None]
         inv = torch.from_numpy(mf)
-        with torch.no_grad():
-            warped = ref.inv_warp_image_batch(x.repeat(len(mf), 1, 1, 1), inv, mode="bilinear")     # Coco.py:279
-            mask = ref.compute_valid_mask(torch.tensor([H, W]), inv_homography=inv, erosion_radius=0)[:, None]
-            heat = fe.run(warped, onlyHeatmap=True, train=False)                                      # export.py:309
-            agg = ref.combine_heatmap(heat, torch.from_numpy(mu)[None], mask, device="cpu")           # export.py:310
+        tm = [time.perf_counter()]
+        fe.net.train(bool(train_bn))
+        try:
+            with torch.no_grad():
+                warped = ref.inv_warp_image_batch(x.repeat(len(mf), 1, 1, 1), inv, mode="bilinear")     # Coco.py:279
+                tm.append(time.perf_counter())
+                mask = ref.compute_valid_mask(torch.tensor([H, W]), inv_homography=inv, erosion_radius=0)[:, None]
+                tm.append(time.perf_counter())
+                heat = fe.run(warped, onlyHeatmap=True, train=False)                                      # export.py:309
+                tm.append(time.perf_counter())
+                agg = ref.combine_heatmap(heat, torch.from_numpy(mu)[None], mask, device="cpu")           # export.py:310
+                tm.append(time.perf_counter())
+        finally:
+            fe.net.eval()
         pts = fe.getPtsFromHeatmap(agg.detach().cpu().squeeze().numpy()).transpose()                # export.py:311
+        tm.append(time.perf_counter())
+        self.stages = {k: round((b - a) * 1e3, 1) for k, a, b in
+                       zip(("warp", "valid_mask", "net_and_flatten", "combine_heatmap", "nms_topk"), tm[:-1], tm[1:])}
         return pts[:wl["topk"]] if wl["topk"] else pts
 
     def extract_image(self, img):
@@ -556,6 +576,32 @@ def run_b200(args):
             dt = (time.perf_counter() - t0) / 5
         line["cpu_baseline"] = {"value": round(1.0 / dt, 4), "unit": UNIT, "cores": arm.cores, "kind": arm.kind,
                                 "sample": arm.sample().replace("per step", "(timed once)")}
+        if ha:
+            line["cpu_baseline"]["stages_ms"] = dict(arm.stages)
+        if ha and args.workload == "c2":
+            # SURVEY 8(d) "report both BN modes": the as-written reference leaves the BN layers in train mode
+            # (model_wrap.py:111); the same image once more that way, next to our opt-in fp32 path for it
+            t0 = time.perf_counter()
+            pts_train = arm.ha_image(imgs_np[0], mu_np, mf_np, train_bn=True)
+            dt_train = time.perf_counter() - t0
+            from pytorch_superpoint_b200 import SuperPointNet_b200 as _Net
+            net_bn = _Net(bn_mode="batch")
+            net_bn.load_state_dict(net.state_dict())
+            ex_bn = HAExporter(net_bn, THR, NMS, TOPK, device=dev, sharded=False)
+            ex_bn.export_image(imgs_host[0], mu_dev[0], mf_dev[0])
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            pts_bn = ex_bn.export_image(imgs_host[0], mu_dev[0], mf_dev[0])
+            dt_bn = time.perf_counter() - t0
+            a = {(int(x), int(y)) for x, y, _ in pts_bn}
+            b = {(int(x), int(y)) for x, y, _ in pts_train}
+            line["train_mode_bn"] = {
+                "cpu_reference_images_per_s": round(1.0 / dt_train, 4),
+                "b200_bn_mode_batch_images_per_s": round(1.0 / dt_bn, 2),
+                "keypoint_jaccard": round(len(a & b) / max(len(a | b), 1), 4),
+                "note": "the as-written reference (BN layers left in train mode: statistics of the 100 views) on the host "
+                        "cores vs SuperPointNet_b200(bn_mode='batch') (fp32 CUDA-core path, csrc/bn.cu), one image each, "
+                        "single calls; informational -- the metric above is the eval-mode product path"}
         if "extract" in line:  # configs[0]: the same single-frame extraction on the host cores, one image
             x1 = structured_images(1, 240, 320, seed=5)[0]
             arm1 = CpuArm(WORKLOADS["c3"])
