@@ -26,6 +26,7 @@ when the homographies are sharded over ranks) -> divide -> threshold + greedy NM
   train_mode_bn (c2, N=1) the as-written reference (BN layers left in train mode) on the host cores next to
              SuperPointNet_b200(bn_mode='batch'), one image each, with the key-point overlap of the two (informational)
   shard_check (N>1) a few images recomputed unsharded on rank 0 outside the timed region vs the sharded result
+  image_sharded (N>1) comparison line: the same batch with images instead of homographies sharded (no collective)
   --impl reference   times that CPU arm as the main line (one full image, all 100 homographies, per step)
 """
 from __future__ import annotations
@@ -537,6 +538,25 @@ def run_b200(args):
             line["shard_check"] = {"images": k, "heat_max_abs": float((heat_sh[:k] - heat_lo).abs().max().item()),
                                    "keypoint_jaccard": round(min(jac), 4),
                                    "note": "sharded (this run) vs unsharded on rank 0: fp32 summation order only"}
+
+    # ---- N > 1: SURVEY 8(e) "alternative noted" -- the same batch with IMAGES sharded instead of homographies (every
+    # rank: its own B / world images with all their views, no collective), as a comparison line outside the timed region
+    if ha and world > 1:
+        img_ex = HAExporter(net, THR, NMS, TOPK, device=dev, chunk=args.chunk, sharded=False)
+        lo_i, hi_i = rank * per_gpu, (rank + 1) * per_gpu
+        im_l, mu_l, mf_l = (t[lo_i:hi_i].contiguous() for t in (imgs_dev, mu_dev, mf_dev))
+
+        def step_img():
+            return img_ex.submit_resident(im_l, mu_l, mf_l)
+
+        for _ in range(3):
+            step_img()
+        n_img = min(args.steps, 10)
+        ms_img = timed(step_img, n_img)
+        line["image_sharded"] = {"value": round(B * n_img / (ms_img / 1e3), 3), "unit": UNIT, "steps": n_img,
+                                 "note": "comparison only: images (not homographies) sharded over the ranks, no "
+                                         "collective; north_star mandates homography sharding + one exchange (the "
+                                         "value above), which also shortens the latency of a single image by world x"}
 
     # ---- second half of the BASELINE metric: single-frame extraction ms/image (configs[2]) next to the CPU arm -----
     if rank == 0 and world == 1 and ha and args.workload == "c2":
