@@ -13,8 +13,9 @@ Workloads (BASELINE.json configs; the default c2 is the configuration the metric
 
 A "step" is one pass of the hot path over one batch of synthetic input: IMAGES x n_gpus images (weak scaling: every
 GPU works on the same number of views per step at every N), each homography-adapted: image warp x100 -> detector
-network -> fused softmax/d2s/un-warp/aggregate -> (NCCL reduce-scatter of the summed planes over the image dimension
-when the homographies are sharded over ranks) -> divide -> threshold + greedy NMS + top-k.  Rank 0 prints ONE JSON line.
+network -> fused softmax/d2s/un-warp/aggregate -> (when the homographies are sharded over ranks: the owner of an image
+adds the partial planes out of its peers' memory over NVLink inside the dividing kernel; SPB200_EXCHANGE=nccl: a
+reduce-scatter over the image dimension) -> divide -> threshold + greedy NMS + top-k.  Rank 0 prints ONE JSON line.
 
   value      images/s with inputs resident in HBM (CUDA events, barrier + synchronize both sides, max over ranks)
   e2e        same metric through HAExporter.submit/collect with pinned HOST images in and HOST key-points out
@@ -505,10 +506,15 @@ def run_b200(args):
                        "homography_sets": "one set per image (datasets/Coco.py:262-276); resident arm: pre-sampled; "
                                           "e2e arm: drawn on the GPU inside every step",
                        "parallelism": (f"homography-sharded x{world}: every rank warps / runs the detector on its rotated "
-                                       f"block of the views of EVERY image ({views_step} views per rank and step), ONE NCCL "
-                                       "reduce-scatter of the [B,2,H,W] planes over the image dimension per step, issued "
-                                       "asynchronously; each rank divides / runs NMS on its B/N images") if ha else
+                                       f"block of the views of EVERY image ({views_step} views per rank and step); ONE "
+                                       "exchange of the [B,2,H,W] planes per step, overlapped with the next step: " +
+                                       ("the owner of an image adds the partial planes straight out of its peers' memory "
+                                        "over NVLink (CUDA IPC) inside the kernel that divides (csrc/peer.cu)"
+                                        if getattr(exporter, "exchange", "") == "peer" else
+                                        "an asynchronous NCCL reduce-scatter over the image dimension") +
+                                       "; each rank runs NMS on its B/N images") if ha else
                                       "single GPU batch",
+                       "exchange": getattr(exporter, "exchange", None) if (ha and world > 1) else None,
                        "l2": "per-pass activation working set (~2 GB) streams through the 126 MB L2 every step "
                              "(inputs larger than L2; no explicit flush)", "ha_chunk": args.chunk},
             "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -87,6 +87,25 @@ int spb_ha_aggregate(const float* semi_nhwc, int cstride, const float* mats_unwa
 int spb_ha_finalize(const float* sums, float* heat, int H, int W, void* stream);
 int spb_ha_finalize_batch(const float* sums /*[B,2,H,W]*/, float* heat /*[B,H,W]*/, int B, int H, int W, void* stream);
 
+/* ---- the exchange of the sharded HA path over NVLink peer memory (replaces nn.DataParallel's gather, export.py:265, and
+ * fuses the reduction over the ranks with export.py:61-63).  One process per GPU of ONE box: every rank keeps its
+ * partial planes sums[B,2,H,W] in a buffer from spb_peer_alloc (cudaMalloc, zeroed), exports a 64-byte CUDA IPC handle
+ * that the others open (spb_peer_open: the peer's buffer mapped into this process).
+ * spb_ha_finalize_peers: heat[b] = (sum_p peer_sums[p][b0+b][0]) / (sum_p peer_sums[p][b0+b][1]) for b < nb, the
+ *   `world` partial planes loaded from peer memory and added in rank order (reduce-scatter + division in one kernel).
+ * spb_peer_signal: after everything enqueued on `stream` so far, store `value` to the n flag addresses (peer memory;
+ *   NULL entries are skipped) with system-scope release.  spb_peer_wait: hold `stream` until the n LOCAL flags are
+ *   >= value (bit t of skip_mask set: flag t is not waited for).  Counters are monotonic per (peer, slot). */
+int spb_peer_alloc(void** ptr, size_t bytes);
+int spb_peer_free(void* ptr);
+int spb_peer_export(void* ptr, unsigned char* handle64);
+int spb_peer_open(const unsigned char* handle64, void** ptr);
+int spb_peer_close(void* ptr);
+int spb_peer_signal(unsigned int* const* flags, int n, unsigned int value, void* stream);
+int spb_peer_wait(const unsigned int* flags, int n, unsigned int value, unsigned int skip_mask, void* stream);
+int spb_ha_finalize_peers(const float* const* peer_sums, int world, int b0, int nb, float* heat, int H, int W,
+                          void* stream);
+
 /* ---- (4) threshold + greedy grid NMS + border removal + top-k -----------------------------------
  * models/model_wrap.py:252-279 `getPtsFromHeatmap` incl. `nms_fast` (117-180) and export.py:322-328
  * (`pts[:top_k]`).  heat [B,H,W].  For image b, pts[b, j, :] = (x, y, conf) for j < counts[b],

@@ -32,6 +32,14 @@ PROTOTYPES = {
     "spb_ha_aggregate": (_i, [_p, _i, _p, _p, _i, _i, _i, _p, _i, _p, _z, _p]),
     "spb_ha_finalize": (_i, [_p, _p, _i, _i, _p]),
     "spb_ha_finalize_batch": (_i, [_p, _p, _i, _i, _i, _p]),
+    "spb_peer_alloc": (_i, [_p, _z]),
+    "spb_peer_free": (_i, [_p]),
+    "spb_peer_export": (_i, [_p, _p]),
+    "spb_peer_open": (_i, [_p, _p]),
+    "spb_peer_close": (_i, [_p]),
+    "spb_peer_signal": (_i, [_p, _i, C.c_uint, _p]),
+    "spb_peer_wait": (_i, [_p, _i, C.c_uint, C.c_uint, _p]),
+    "spb_ha_finalize_peers": (_i, [_p, _i, _i, _i, _p, _i, _i, _p]),
     "spb_nms_workspace_bytes": (_z, [_i, _i, _i, _i]),
     "spb_get_pts_from_heatmap": (_i, [_p, _i, _i, _i, _f, _i, _i, _i, _i, _p, _p, _p, _p, _z, _p]),
     "spb_sample_desc_from_points": (_i, [_p, _i, _p, _p, _i, _i, _i, _i, _i, _p, _p]),

@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libspb200.so")
-SOURCES = ["warp.cu", "heat.cu", "ha_fast.cu", "nms.cu", "desc.cu", "match.cu", "sampler.cu", "ingest.cu", "conv_simt.cu", "bn.cu", "conv_tc.cu", "conv_tc2.cu", "conv_s3.cu", "net.cu"]
+SOURCES = ["warp.cu", "heat.cu", "peer.cu", "ha_fast.cu", "nms.cu", "desc.cu", "match.cu", "sampler.cu", "ingest.cu", "conv_simt.cu", "bn.cu", "conv_tc.cu", "conv_tc2.cu", "conv_s3.cu", "net.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default", "--expt-relaxed-constexpr",
               "-Xptxas", "-v" if os.environ.get("SPB200_VERBOSE") else "-warn-spills"]

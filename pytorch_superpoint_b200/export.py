@@ -18,21 +18,25 @@ import torch.distributed as dist
 from . import ops
 from .homographies import make_ha_homographies, sample_ha_homographies_device  # noqa: F401
 from .net import SuperPointNet_b200
-from .sharding import owned_images, plan_batch, sharded_heatmap_sums, world_info
+from .sharding import PeerExchange, PeerUnavailable, owned_images, plan_batch, same_host, sharded_heatmap_sums, world_info
 
 __all__ = ["HAExporter", "export_detector_homoAdapt_b200"]
 
 
 class HAExporter:
     """One process per GPU.  With ``torch.distributed`` initialised (NCCL) the homographies of every image are
-    sharded over the ranks (``sharding.plan_batch``: rotated view blocks) and combined by ONE collective per batch
-    (``sharding.exchange_sums``: a reduce-scatter over the image dimension, issued asynchronously so that it and the
-    division / NMS / top-k of batch i run under the warps and convolutions of batch i+1); otherwise everything runs
-    locally.  ``subpixel_patch`` > 0 adds the soft-argmax refinement of export.py:314-319 on the device."""
+    sharded over the ranks (``sharding.plan_batch``: rotated view blocks) and combined by ONE exchange per batch that
+    runs, with the division / NMS / top-k of batch i, under the warps and convolutions of batch i+1.
+    ``exchange``: ``'peer'`` -- the owner of an image adds the partial planes straight out of its peers' memory over
+    NVLink inside the kernel that divides (``sharding.PeerExchange``, CUDA IPC, one box); ``'nccl'`` -- an asynchronous
+    ``reduce_scatter`` over the image dimension (``sharding.exchange_sums``); ``'auto'`` (default; env
+    ``SPB200_EXCHANGE`` overrides): peer memory when every rank runs on this host, NCCL otherwise.  Without
+    ``torch.distributed`` everything runs locally.  ``subpixel_patch`` > 0 adds the soft-argmax refinement of
+    export.py:314-319 on the device."""
 
     def __init__(self, net: SuperPointNet_b200, conf_thresh=0.015, nms_dist=4, top_k=600, border_remove=4,
                  device: Optional[torch.device] = None, group=None, chunk: int = 0, subpixel_patch: int = 0,
-                 sharded: bool = True):
+                 sharded: bool = True, exchange: str = "auto"):
         if not torch.cuda.is_available():
             raise RuntimeError("HAExporter needs a CUDA device (sm_100a); there is no CPU fallback")
         self.net = net
@@ -42,6 +46,10 @@ class HAExporter:
         self.chunk = chunk
         self.subpixel_patch = int(subpixel_patch)
         self.sharded = bool(sharded)  # False: ignore torch.distributed (a purely local exporter, e.g. a cross-check)
+        exchange = os.environ.get("SPB200_EXCHANGE", exchange)
+        if exchange not in ("auto", "peer", "nccl"):
+            raise ValueError(f"exchange must be 'auto', 'peer' or 'nccl', got {exchange!r}")
+        self.exchange = exchange  # resolved to 'peer' / 'nccl' when the first multi-rank buffers are built (collective)
         self._bufs = {}
         self._plans = {}
         self._side = self._copy = None
@@ -60,16 +68,31 @@ class HAExporter:
             lo, hi = owned_images(B, rank, world)
             nown = max(hi - lo, 1)
             f32 = dict(device=dev, dtype=torch.float32)
-            slots = [dict(sums=torch.empty((B, 2, H, W), **f32),        # this rank's partial planes of the batch
-                          owned=torch.empty((nown, 2, H, W), **f32),    # reduce-scatter output
+            for old in self._bufs.values():  # one batch shape at a time: release the previous shape's peer mappings
+                if old.get("peer") is not None:
+                    old["peer"].close()
+            peer = None
+            if world > 1:
+                auto = self.exchange == "auto"
+                if auto:
+                    self.exchange = "peer" if same_host(self.group) else "nccl"
+                if self.exchange == "peer":
+                    try:
+                        peer = PeerExchange(B, H, W, dev, self.group)  # collective: all ranks build the same shapes
+                    except PeerUnavailable:
+                        if not auto:
+                            raise
+                        self.exchange = "nccl"  # (every rank takes this branch: the constructor agrees on it)
+            slots = [dict(sums=peer.sums[i] if peer is not None else torch.empty((B, 2, H, W), **f32),  # partial planes
+                          owned=None if peer is not None else torch.empty((nown, 2, H, W), **f32),  # reduce-scatter out
                           heat=torch.empty((nown, H, W), **f32),
                           dxdy=torch.zeros((nown, cap, 2), **f32),
                           pts_host=torch.empty((nown, cap, 3), dtype=torch.float32).pin_memory(),
                           dxdy_host=torch.empty((nown, cap, 2), dtype=torch.float32).pin_memory(),
                           cnt_host=torch.empty((nown,), dtype=torch.int32).pin_memory(),
-                          done=None, own=(lo, hi), B=B) for _ in range(2)]
+                          done=None, own=(lo, hi), B=B) for i in range(2)]
             self._bufs = {key: dict(img=[torch.empty((B, H, W), **f32) for _ in range(2)], img_free=[None, None], kin=0,
-                                    slots=slots, cap=cap, k=0)}
+                                    slots=slots, cap=cap, k=0, peer=peer)}
             if self._side is None:
                 self._side = torch.cuda.Stream(device=dev)
                 self._copy = torch.cuda.Stream(device=dev)
@@ -118,14 +141,22 @@ class HAExporter:
         shared = mats_unwarp.dim() == 3
         N = mats_unwarp.shape[-3]
         plan, plan_dev = self.plan(B, N, H, W, shared)
-        slot = buf["slots"][buf["k"] & 1]
+        step = buf["k"]
+        slot = buf["slots"][step & 1]
         buf["k"] += 1
+        peer = buf["peer"]
         main = torch.cuda.current_stream()
         if slot["done"] is not None:
             main.wait_event(slot["done"])  # the exchange / side stream of two batches ago still reads this slot
         partial_fn = self._partial_fn(imgs_dev, mats_unwarp, mats_fwd, plan_dev)
-        owned, work, _ = sharded_heatmap_sums(partial_fn, B, N, slot["sums"], group=self.group, plan=plan,
-                                              out=slot["owned"], async_op=True)
+        if peer is not None:
+            peer.wait_reusable(step, main.cuda_stream)  # every owner has read this slot's planes of two batches ago
+            owned, work, _ = sharded_heatmap_sums(partial_fn, B, N, slot["sums"], group=self.group, plan=plan,
+                                                  exchange=lambda sums, pl: (None, None))
+            peer.publish(step, main.cuda_stream)        # this rank's partial planes of the batch are complete
+        else:
+            owned, work, _ = sharded_heatmap_sums(partial_fn, B, N, slot["sums"], group=self.group, plan=plan,
+                                                  out=slot["owned"], async_op=True)
         ready = torch.cuda.Event()
         ready.record(main)
         lo, hi = plan.own
@@ -136,10 +167,13 @@ class HAExporter:
         with torch.cuda.stream(side):
             if work is not None:
                 work.wait()  # the side stream (not the main one) waits for the collective
+            if peer is not None:  # reduce over the ranks + export.py:63 in one kernel, straight from peer memory
+                peer.finalize(step, lo, hi, slot["heat"], side.cuda_stream)
             if hi > lo:
                 heat = slot["heat"][:hi - lo]
-                _lib.check(L.spb_ha_finalize_batch(owned.data_ptr(), heat.data_ptr(), hi - lo, H, W, side.cuda_stream),
-                           "ha_finalize")  # export.py:63
+                if peer is None:
+                    _lib.check(L.spb_ha_finalize_batch(owned.data_ptr(), heat.data_ptr(), hi - lo, H, W,
+                                                       side.cuda_stream), "ha_finalize")  # export.py:63
                 pts, counts, _ = ops.get_pts_from_heatmap_device(heat, self.conf_thresh, self.nms_dist,
                                                                  self.border_remove, self.top_k, buf["cap"])
                 if self.subpixel_patch:  # model_wrap.py:200-234: all owned images in ONE launch, no host round trip
@@ -215,6 +249,14 @@ class HAExporter:
     def export_image(self, img_host: torch.Tensor, mats_unwarp: torch.Tensor, mats_fwd: torch.Tensor) -> np.ndarray:
         """One image -> float64 [K,3]; with several ranks only rank 0 returns the points (others None)."""
         return self.export_batch([img_host], mats_unwarp, mats_fwd)[0]
+
+    def close(self):
+        """Collective when the peer exchange is active: unmap / free the shared buffers (all ranks call it)."""
+        for buf in self._bufs.values():
+            if buf.get("peer") is not None:
+                buf["peer"].close()
+                buf["peer"] = None
+        self._bufs = {}
 
     def last_heat(self, B, H, W) -> torch.Tensor:
         """Heat-maps [owned,H,W] of the most recent batch of this shape (valid after its collect())."""

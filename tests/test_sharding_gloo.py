@@ -155,3 +155,28 @@ def test_balanced_view_plan_partitions_every_pair_once():
         if B % world == 0:
             assert max(totals) == min(totals) == B * N // world
         assert max(totals) - min(totals) <= max(1, B % world)
+
+
+def test_exchange_hook_replaces_the_collective():
+    """``sharded_heatmap_sums(..., exchange=fn)``: the partial sums are computed exactly as for the collective path and
+    handed to ``fn`` (the peer-memory exchange of the GPU path, sharding.PeerExchange) instead of exchange_sums."""
+    from pytorch_superpoint_b200.sharding import plan_batch, sharded_heatmap_sums
+    B, N, H, W = 3, 5, 4, 6
+    sums = torch.full((B, 2, H, W), 7.0)
+    seen = {}
+
+    def partial_fn(p, out):
+        for j in range(p.nb):
+            n = int(p.view_offsets[j + 1] - p.view_offsets[j])
+            if p.accumulate:
+                out[p.b0 + j] += n
+            else:
+                out[p.b0 + j] = n
+
+    def exchange(s, plan):
+        seen["sums"], seen["plan"] = s.clone(), plan
+        return "owned", "work"
+
+    owned, work, plan = sharded_heatmap_sums(partial_fn, B, N, sums, plan=plan_batch(B, N, 0, 1, 2), exchange=exchange)
+    assert (owned, work) == ("owned", "work") and seen["plan"] is plan
+    assert torch.equal(seen["sums"], torch.full((B, 2, H, W), float(N)))  # every view of every image counted once
