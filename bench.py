@@ -638,6 +638,8 @@ def run_b200(args):
             line["extract"]["cpu_kind"] = arm1.kind
     if world > 1:
         try:
+            if ha:
+                exporter.close()  # collective: unmap / free the peer-memory exchange buffers
             dist.barrier()
             dist.destroy_process_group()
         except Exception:

@@ -371,4 +371,5 @@ def export_detector_homoAdapt_b200(config, output_dir, args=None, loader=None, n
         t = torch.tensor([count], device=exporter.device)
         dist.all_reduce(t, group=exporter.group)
         count = int(t.item())
+    exporter.close()  # (collective with the peer-memory exchange: unmap / free the shared buffers)
     return count
