@@ -16,11 +16,13 @@
 // memory and the cluster barrier separates the phases.  Bitmap words come from warp ballots, windows
 // from funnel shifts.  Survivors are compacted with their 64-bit sort key and ranked by a second,
 // grid-wide count-greater kernel (keys are unique, so rank == final position).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace spb {
 
-constexpr int kNmsThreads = 1024;
+constexpr int kNmsThreads = 1024;  // threads per CTA for small batches; large batches run 512 / 256 (more CTAs per SM)
 constexpr int kMaxDist = 15;  // window bits (2d+1) must fit a 32-bit word
 constexpr int kMaxCluster = 8;
 
@@ -71,11 +73,12 @@ __device__ __forceinline__ void dsmem_store(const void* local, unsigned rank, un
   asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(ra), "r"(v) : "memory");
 }
 
-__global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(NmsParams p) {
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS) nms_kernel(NmsParams p) {
   extern __shared__ unsigned s_dyn[];
   __shared__ int s_flag[kMaxCluster];
   __shared__ int s_cnt[kMaxCluster];
-  __shared__ int s_scan[kNmsThreads / 32];
+  __shared__ int s_scan[THREADS / 32];
   const unsigned crank = cluster_rank(), csize = cluster_size();
   const int b = blockIdx.x / csize;
   const int H = p.H, W = p.W, d = p.d, ww = p.ww;
@@ -85,13 +88,13 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(NmsParams p) {
   unsigned* kept = s_dyn + lrows * ww;
   unsigned* keys_s = s_dyn + 2 * lrows * ww;      // [lrows][W] order-preserving keys (band + halo) when keys_smem
   const float* heat = p.heat + (long long)b * H * W;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = kNmsThreads / 32;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = THREADS / 32;
   const int wpr = (W + 31) >> 5;  // data words per row
   const int ntask = nr * wpr;
 
-  for (int i = tid; i < 2 * lrows * ww; i += kNmsThreads) s_dyn[i] = 0u;
+  for (int i = tid; i < 2 * lrows * ww; i += THREADS) s_dyn[i] = 0u;
   if (p.keys_smem)
-    for (int i = tid; i < lrows * W; i += kNmsThreads) {
+    for (int i = tid; i < lrows * W; i += THREADS) {
       const int yy = y0 - d + i / W;
       keys_s[i] = (yy >= 0 && yy < H) ? ord_bits(__ldg(heat + (long long)yy * W + i % W)) : 0u;
     }
@@ -105,9 +108,9 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(NmsParams p) {
     if (d == 0 || nr == 0) return;
     const int n = d * ww;
     if (crank > 0)  // my first d rows -> bottom halo of the band above (which is always a full band)
-      for (int i = tid; i < n; i += kNmsThreads) dsmem_store(bm + (d + p.rb) * ww + i, crank - 1, bm[d * ww + i]);
+      for (int i = tid; i < n; i += THREADS) dsmem_store(bm + (d + p.rb) * ww + i, crank - 1, bm[d * ww + i]);
     if (crank + 1 < csize && y1 < H)  // my last d rows -> top halo of the band below
-      for (int i = tid; i < n; i += kNmsThreads) dsmem_store(bm + i, crank + 1, bm[nr * ww + i]);
+      for (int i = tid; i < n; i += THREADS) dsmem_store(bm + i, crank + 1, bm[nr * ww + i]);
   };
 
   // threshold (model_wrap.py:261): fp32 compare, NaN never passes
@@ -326,10 +329,21 @@ int spb_get_pts_from_heatmap(const float* heat, int B, int H, int W, float conf_
   p.keys = static_cast<unsigned long long*>(ws);
   p.nkept = reinterpret_cast<int*>(p.keys + (size_t)B * p.maxk);
   cudaStream_t st = as_stream(stream);
-  SPB_CHECK_CUDA(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap));
+  // One CTA of 1024 threads per SM holds 148 / C images at a time; when the batch has more CTAs than that, smaller
+  // CTAs (2 or 4 per SM, registers and shared memory permitting) keep other images running while one waits at its
+  // cluster barrier.  SPB_NMS_THREADS overrides (A/B measurements).
+  int threads = kNmsThreads;
+  if ((long long)B * C > kNumSMs && smem <= 100 * 1024) threads = 512;
+  if ((long long)B * C > 2 * kNumSMs && smem <= 50 * 1024) threads = 256;
+  if (const char* e = getenv("SPB_NMS_THREADS")) {
+    const int t = atoi(e);
+    if (t == 256 || t == 512 || t == 1024) threads = t;
+  }
+  auto kern = threads == 1024 ? nms_kernel<1024> : threads == 512 ? nms_kernel<512> : nms_kernel<256>;
+  SPB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(B * C);
-  cfg.blockDim = dim3(kNmsThreads);
+  cfg.blockDim = dim3(threads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -339,7 +353,7 @@ int spb_get_pts_from_heatmap(const float* heat, int B, int H, int W, float conf_
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  SPB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, nms_kernel, p));
+  SPB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
   SPB_CHECK_LAUNCH();
   dim3 grid(ceil_div(p.maxk, 256), B);
   rank_scatter_kernel<<<grid, 256, 0, st>>>(heat, H, W, p.keys, p.nkept, p.maxk, top_k, capacity, pts, counts, total);
