@@ -225,6 +225,229 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) nms_kernel(NmsParams 
   cluster_barrier();  // nobody leaves while a peer may still write into its shared memory
 }
 
+// ------------------------------------------------------------------------------------------------
+// The same rounds with SEPARABLE window maxima (the default): per round
+//   (A) every pixel of a row that can matter gets the leftmost maximum of the undecided keys in [x-d, x+d]
+//       (key + column offset, shared by the 2d+1 output rows that look at this row);
+//   (B) an undecided pixel wins iff the topmost maximum over the rows y-d .. y+d of (A) is itself -- the total order
+//       (key desc, row-major index asc) again, so the selected set is identical to nms_kernel's phase 2;
+//   (C) the winners of the round are dilated by d on the BITMAP (funnel shifts, one thread per word) and cleared
+//       from the undecided set together with everything they suppress -- nms_kernel's phase 1 without a per-pixel
+//       loop.
+// A dense candidate field (a random-init network: 34 k of 76.8 k pixels above the threshold) costs ~90 instructions
+// per pixel and round instead of a divergent scan of up to (2d+1)^2 neighbours per candidate.
+// ------------------------------------------------------------------------------------------------
+template <int THREADS, int DT>  // DT: compile-time nms distance (the tap loops unroll, their loads overlap) or 0 = p.d
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS) nms2_kernel(NmsParams p) {
+  extern __shared__ unsigned s_dyn[];
+  __shared__ int s_flag[kMaxCluster];
+  __shared__ int s_cnt[kMaxCluster];
+  __shared__ int s_scan[THREADS / 32];
+  const unsigned crank = cluster_rank(), csize = cluster_size();
+  const int b = blockIdx.x / csize;
+  const int H = p.H, W = p.W, d = DT ? DT : p.d, ww = p.ww;
+  const int y0 = crank * p.rb, y1 = min(H, y0 + p.rb), nr = max(y1 - y0, 0);
+  const int lrows = p.rb + 2 * d;  // local rows: [0,d) top halo, [d,d+nr) own, then bottom halo
+  unsigned* und = s_dyn;           // [lrows][ww] undecided
+  unsigned* kept = und + lrows * ww;
+  unsigned* newk = kept + lrows * ww;   // winners of the current round
+  unsigned* hdil = newk + lrows * ww;   // newk dilated horizontally
+  unsigned* rk = hdil + lrows * ww;     // [lrows][W] leftmost maximum of the undecided keys in [x-d, x+d] (0: none)
+  unsigned char* rj = reinterpret_cast<unsigned char*>(rk + lrows * W);  // [lrows][W] its window offset 0 .. 2d
+  unsigned* keys_s = reinterpret_cast<unsigned*>(rj + (((size_t)lrows * W + 15) & ~(size_t)15));  // optional
+  const float* heat = p.heat + (long long)b * H * W;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = THREADS / 32;
+  const int wpr = (W + 31) >> 5;
+  const int ntask = nr * wpr, nall = lrows * wpr;
+
+  for (int i = tid; i < 4 * lrows * ww; i += THREADS) s_dyn[i] = 0u;
+  if (p.keys_smem)
+    for (int i = tid; i < lrows * W; i += THREADS) {
+      const int yy = y0 - d + i / W;
+      keys_s[i] = (yy >= 0 && yy < H) ? ord_bits(__ldg(heat + (long long)yy * W + i % W)) : 0u;
+    }
+  cluster_barrier();
+
+  // key of local row lr (0 .. lrows-1), column xx; only called where an undecided bit is set (inside the image)
+  auto key_l = [&](int lr, int xx) -> unsigned {
+    return p.keys_smem ? keys_s[lr * W + xx] : ord_bits(__ldg(heat + (long long)(y0 - d + lr) * W + xx));
+  };
+  auto push_halo = [&](unsigned* bm) {
+    if (d == 0 || nr == 0) return;
+    const int n = d * ww;
+    if (crank > 0)
+      for (int i = tid; i < n; i += THREADS) dsmem_store(bm + (d + p.rb) * ww + i, crank - 1, bm[d * ww + i]);
+    if (crank + 1 < csize && y1 < H)
+      for (int i = tid; i < n; i += THREADS) dsmem_store(bm + i, crank + 1, bm[nr * ww + i]);
+  };
+
+  for (int t = warp; t < ntask; t += nwarp) {
+    const int ly = t / wpr, w = t % wpr, x = w * 32 + lane, y = y0 + ly;
+    const bool c = x < W && heat[(long long)y * W + x] >= p.thr;
+    const unsigned m = __ballot_sync(0xffffffffu, c);
+    if (lane == 0) und[(ly + d) * ww + w + 1] = m;
+  }
+  __syncthreads();
+  push_halo(und);
+  cluster_barrier();
+
+  while (true) {
+    // (A) row maxima for every local row / word some own undecided pixel looks at
+    for (int t = warp; t < nall; t += nwarp) {
+      const int lr = t / wpr, w = t % wpr, x = w * 32 + lane;
+      unsigned need = 0u;  // undecided bits of OWN rows within d rows of lr, this word
+      for (int q = max(lr - d, d); q <= min(lr + d, d + nr - 1); ++q) need |= und[q * ww + w + 1];
+      if (need == 0u) continue;
+      unsigned best = 0u, bj = 0u;
+      if (x < W) {
+        const unsigned bits = window_bits(und + lr * ww, x, d);
+        if (DT) {  // all taps issued at once (predicated loads), then the compare chain
+          unsigned k[2 * DT + 1];
+#pragma unroll
+          for (int j = 0; j <= 2 * DT; ++j) k[j] = ((bits >> j) & 1u) ? key_l(lr, x - DT + j) : 0u;
+#pragma unroll
+          for (int j = 0; j <= 2 * DT; ++j)
+            if (k[j] > best) {  // strict: the leftmost of equal keys stays
+              best = k[j];
+              bj = (unsigned)j;
+            }
+        } else {
+          unsigned rest = bits;
+          while (rest) {
+            const int j = __ffs(rest) - 1;
+            rest &= rest - 1;
+            const unsigned kk = key_l(lr, x - d + j);
+            if (kk > best) {
+              best = kk;
+              bj = (unsigned)j;
+            }
+          }
+        }
+        rk[lr * W + x] = best;
+        rj[lr * W + x] = (unsigned char)bj;
+      }
+    }
+    __syncthreads();
+    // (B) winners: the topmost row maximum over y-d .. y+d is this pixel itself
+    for (int t = warp; t < ntask; t += nwarp) {
+      const int ly = t / wpr, w = t % wpr, x = w * 32 + lane;
+      const unsigned word = und[(ly + d) * ww + w + 1];
+      unsigned m = 0u;
+      if (word != 0u) {
+        bool win = (word >> lane) & 1u;
+        if (win) {
+          unsigned best = 0u;
+          int br = 0, bj = 0;
+          if (DT) {
+            unsigned k[2 * DT + 1], jj[2 * DT + 1];
+#pragma unroll
+            for (int r = 0; r <= 2 * DT; ++r) {
+              k[r] = rk[(ly + r) * W + x];
+              jj[r] = rj[(ly + r) * W + x];
+            }
+#pragma unroll
+            for (int r = 0; r <= 2 * DT; ++r)
+              if (k[r] > best) {  // strict: the topmost of equal keys stays
+                best = k[r];
+                br = r;
+                bj = (int)jj[r];
+              }
+          } else {
+            for (int r = 0; r <= 2 * d; ++r) {
+              const unsigned kk = rk[(ly + r) * W + x];
+              if (kk > best) {
+                best = kk;
+                br = r;
+                bj = rj[(ly + r) * W + x];
+              }
+            }
+          }
+          win = br == d && bj == d;  // (best is then this pixel's own key)
+        }
+        m = __ballot_sync(0xffffffffu, win);
+      }
+      if (lane == 0) {
+        newk[(ly + d) * ww + w + 1] = m;
+        if (m) kept[(ly + d) * ww + w + 1] |= m;
+      }
+    }
+    __syncthreads();
+    push_halo(newk);
+    cluster_barrier();
+    // (C) clear the winners and everything within d of a winner from the undecided set (bitmap dilation)
+    for (int i = tid; i < nall; i += THREADS) {
+      const int lr = i / wpr, w = i % wpr;
+      const unsigned* row = newk + lr * ww + w + 1;
+      const unsigned cur = row[0], prev = row[-1], next = row[1];
+      unsigned o = cur;
+      if (cur | prev | next)
+        for (int s = 1; s <= d; ++s) o |= __funnelshift_l(prev, cur, s) | __funnelshift_r(cur, next, s);
+      hdil[lr * ww + w + 1] = o;
+    }
+    __syncthreads();
+    int any = 0;
+    for (int i = tid; i < ntask; i += THREADS) {
+      const int ly = i / wpr, w = i % wpr;
+      unsigned u = und[(ly + d) * ww + w + 1];
+      if (u) {
+        unsigned v = 0u;
+        for (int r = 0; r <= 2 * d; ++r) v |= hdil[(ly + r) * ww + w + 1];
+        u &= ~v;
+        und[(ly + d) * ww + w + 1] = u;
+        any |= (u != 0u);
+      }
+    }
+    any = __syncthreads_or(any);
+    push_halo(und);
+    if (tid < (int)csize) dsmem_store(&s_flag[crank], tid, (unsigned)any);
+    cluster_barrier();
+    int go = 0;
+    for (unsigned i = 0; i < csize; ++i) go |= s_flag[i];
+    if (!go) break;
+  }
+
+  // border removal AFTER suppression (model_wrap.py:274-278), compaction with sort keys
+  int mycount = 0;
+  for (int t = warp; t < ntask; t += nwarp) {
+    const int ly = t / wpr, w = t % wpr, x = w * 32 + lane, y = y0 + ly;
+    const bool k = ((kept[(ly + d) * ww + w + 1] >> lane) & 1u) && x >= p.border && x < W - p.border &&
+                   y >= p.border && y < H - p.border;
+    mycount += __popc(__ballot_sync(0xffffffffu, k));
+  }
+  if (lane == 0) s_scan[warp] = mycount;
+  __syncthreads();
+  if (tid == 0) {
+    int acc = 0;
+    for (int i = 0; i < nwarp; ++i) {
+      const int c = s_scan[i];
+      s_scan[i] = acc;
+      acc += c;
+    }
+    for (unsigned i = 0; i < csize; ++i) dsmem_store(&s_cnt[crank], i, (unsigned)acc);
+  }
+  cluster_barrier();
+  int cta_base = 0, total = 0;
+  for (unsigned i = 0; i < csize; ++i) {
+    if (i < crank) cta_base += s_cnt[i];
+    total += s_cnt[i];
+  }
+  if (crank == 0 && tid == 0) p.nkept[b] = total < p.maxk ? total : p.maxk;
+  int base = cta_base + s_scan[warp];
+  unsigned long long* keys = p.keys + (long long)b * p.maxk;
+  for (int t = warp; t < ntask; t += nwarp) {
+    const int ly = t / wpr, w = t % wpr, x = w * 32 + lane, y = y0 + ly;
+    const bool k = ((kept[(ly + d) * ww + w + 1] >> lane) & 1u) && x >= p.border && x < W - p.border &&
+                   y >= p.border && y < H - p.border;
+    const unsigned m = __ballot_sync(0xffffffffu, k);
+    if (k) {
+      const int slot = base + __popc(m & ((1u << lane) - 1u));
+      if (slot < p.maxk) keys[slot] = ((unsigned long long)key_l(ly + d, x) << 32) | (unsigned)(y * W + x);
+    }
+    base += __popc(m);
+  }
+  cluster_barrier();  // nobody leaves while a peer may still write into its shared memory
+}
+
 // rank = number of keys greater than mine; final order = key descending
 // (confidence desc, then larger row-major index first: model_wrap.py:177-178 then 271-272 with stable sorts)
 __global__ void __launch_bounds__(256) rank_scatter_kernel(const float* __restrict__ heat, int H, int W,
@@ -317,13 +540,27 @@ int spb_get_pts_from_heatmap(const float* heat, int B, int H, int W, float conf_
   p.ww = ceil_div(W, 32) + 2;
   const int C = nms_cluster(H, nms_dist, p.rb);
   const size_t lrows = (size_t)p.rb + 2 * nms_dist;
-  const size_t bm_bytes = 2 * lrows * p.ww * sizeof(unsigned), key_bytes = lrows * W * sizeof(unsigned);
+  // algo 1 (default): separable window maxima (nms2_kernel); 0: per-candidate window scans (nms_kernel).
+  int algo = 1;
+  if (const char* e = getenv("SPB_NMS_ALGO")) algo = atoi(e) != 0;
+  const size_t key_bytes = lrows * W * sizeof(unsigned);
   const size_t cap = 200 * 1024;
+  size_t bm_bytes = 2 * lrows * p.ww * sizeof(unsigned);
+  if (algo == 1) {  // + newk, hdil bitmaps, row maxima (key + offset)
+    const size_t need = 4 * lrows * p.ww * sizeof(unsigned) + key_bytes + ((lrows * W + 15) & ~(size_t)15);
+    if (need > cap)
+      algo = 0;  // a band of this image does not fit with the row maxima: the scan kernel needs less
+    else
+      bm_bytes = need;
+  }
   if (bm_bytes > cap) {
     set_error("spb_get_pts_from_heatmap: image %dx%d needs %zu B of bitmap shared memory per CTA (> 200 KB)", H, W, bm_bytes);
     return SPB_EINVAL;
   }
-  p.keys_smem = (bm_bytes + key_bytes <= cap) ? 1 : 0;
+  // the keys of band + halo live in shared memory when two CTAs of this size still fit on an SM (or, for the scan
+  // kernel, whenever they fit at all)
+  const bool one_cta_per_sm = (long long)B * C <= kNumSMs;
+  p.keys_smem = (bm_bytes + key_bytes <= (algo == 1 && !one_cta_per_sm ? 100 * 1024 : cap)) ? 1 : 0;
   const size_t smem = bm_bytes + (p.keys_smem ? key_bytes : 0);
   p.maxk = nms_maxk(H, W, nms_dist);
   p.keys = static_cast<unsigned long long*>(ws);
@@ -339,7 +576,13 @@ int spb_get_pts_from_heatmap(const float* heat, int B, int H, int W, float conf_
     const int t = atoi(e);
     if (t == 256 || t == 512 || t == 1024) threads = t;
   }
-  auto kern = threads == 1024 ? nms_kernel<1024> : threads == 512 ? nms_kernel<512> : nms_kernel<256>;
+  void (*kern)(NmsParams);
+  if (algo == 1 && nms_dist == 4)  // the reference's distance: unrolled taps
+    kern = threads == 1024 ? nms2_kernel<1024, 4> : threads == 512 ? nms2_kernel<512, 4> : nms2_kernel<256, 4>;
+  else if (algo == 1)
+    kern = threads == 1024 ? nms2_kernel<1024, 0> : threads == 512 ? nms2_kernel<512, 0> : nms2_kernel<256, 0>;
+  else
+    kern = threads == 1024 ? nms_kernel<1024> : threads == 512 ? nms_kernel<512> : nms_kernel<256>;
   SPB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(B * C);
