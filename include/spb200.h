@@ -116,6 +116,13 @@ size_t spb_nms_workspace_bytes(int B, int H, int W, int nms_dist);
 int spb_get_pts_from_heatmap(const float* heat, int B, int H, int W, float conf_thresh, int nms_dist,
                              int border_remove, int top_k, int capacity, float* pts, int* counts, int* total,
                              void* ws, size_t ws_bytes, void* stream);
+/* The same with the CTA size of the NMS kernel chosen by the caller: 0 = automatic (1024 threads; 512 when the batch
+ * has more clusters than SMs, so that a second image runs on an SM while the first waits at its cluster barrier --
+ * best when the launch has the GPU to itself), 1024 = for a launch that runs BESIDE other kernels (the exporter's side
+ * stream under the convolutions of the next batch: smaller CTAs take the SMs away from them for longer). */
+int spb_get_pts_from_heatmap_ex(const float* heat, int B, int H, int W, float conf_thresh, int nms_dist,
+                                int border_remove, int top_k, int capacity, float* pts, int* counts, int* total,
+                                void* ws, size_t ws_bytes, int cta_threads, void* stream);
 
 /* ---- (5) descriptor sampling -----------------------------------------------------------------------
  * models/model_wrap.py:281-299 `sample_desc_from_points(coarse_desc, pts)`: bilinear

@@ -42,6 +42,7 @@ PROTOTYPES = {
     "spb_ha_finalize_peers": (_i, [_p, _i, _i, _i, _p, _i, _i, _p]),
     "spb_nms_workspace_bytes": (_z, [_i, _i, _i, _i]),
     "spb_get_pts_from_heatmap": (_i, [_p, _i, _i, _i, _f, _i, _i, _i, _i, _p, _p, _p, _p, _z, _p]),
+    "spb_get_pts_from_heatmap_ex": (_i, [_p, _i, _i, _i, _f, _i, _i, _i, _i, _p, _p, _p, _p, _z, _i, _p]),
     "spb_sample_desc_from_points": (_i, [_p, _i, _p, _p, _i, _i, _i, _i, _i, _p, _p]),
     "spb_sample_desc_from_points_ex": (_i, [_p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _p, _p]),
     "spb_roi_soft_argmax": (_i, [_p, _i, _i, _i, _p, _i, _p, _p, _p]),

@@ -521,9 +521,17 @@ size_t spb_nms_workspace_bytes(int B, int H, int W, int nms_dist) {
 int spb_get_pts_from_heatmap(const float* heat, int B, int H, int W, float conf_thresh, int nms_dist,
                              int border_remove, int top_k, int capacity, float* pts, int* counts, int* total,
                              void* ws, size_t ws_bytes, void* stream) {
+  return spb_get_pts_from_heatmap_ex(heat, B, H, W, conf_thresh, nms_dist, border_remove, top_k, capacity, pts, counts,
+                                     total, ws, ws_bytes, 0, stream);
+}
+
+int spb_get_pts_from_heatmap_ex(const float* heat, int B, int H, int W, float conf_thresh, int nms_dist,
+                                int border_remove, int top_k, int capacity, float* pts, int* counts, int* total,
+                                void* ws, size_t ws_bytes, int cta_threads, void* stream) {
   SPB_CHECK_ARG(heat && pts && counts && ws);
   SPB_CHECK_ARG(B >= 1 && H >= 1 && W >= 1 && capacity >= 1 && border_remove >= 0);
   SPB_CHECK_ARG(nms_dist >= 0 && nms_dist <= kMaxDist);
+  SPB_CHECK_ARG(cta_threads == 0 || cta_threads == 256 || cta_threads == 512 || cta_threads == 1024);
   SPB_CHECK_ARG((long long)H * W < (1LL << 31));
   if (ws_bytes < spb_nms_workspace_bytes(B, H, W, nms_dist)) {
     set_error("spb_get_pts_from_heatmap: workspace %zu < %zu bytes", ws_bytes, spb_nms_workspace_bytes(B, H, W, nms_dist));
@@ -559,7 +567,7 @@ int spb_get_pts_from_heatmap(const float* heat, int B, int H, int W, float conf_
   }
   // the keys of band + halo live in shared memory when two CTAs of this size still fit on an SM (or, for the scan
   // kernel, whenever they fit at all)
-  const bool one_cta_per_sm = (long long)B * C <= kNumSMs;
+  const bool one_cta_per_sm = (long long)B * C <= kNumSMs || cta_threads == 1024;
   p.keys_smem = (bm_bytes + key_bytes <= (algo == 1 && !one_cta_per_sm ? 100 * 1024 : cap)) ? 1 : 0;
   const size_t smem = bm_bytes + (p.keys_smem ? key_bytes : 0);
   p.maxk = nms_maxk(H, W, nms_dist);
@@ -570,8 +578,12 @@ int spb_get_pts_from_heatmap(const float* heat, int B, int H, int W, float conf_
   // CTAs (2 or 4 per SM, registers and shared memory permitting) keep other images running while one waits at its
   // cluster barrier.  SPB_NMS_THREADS overrides (A/B measurements).
   int threads = kNmsThreads;
-  if ((long long)B * C > kNumSMs && smem <= 100 * 1024) threads = 512;
-  if ((long long)B * C > 2 * kNumSMs && smem <= 50 * 1024) threads = 256;
+  if (cta_threads == 1024 || cta_threads == 512 || cta_threads == 256) {
+    threads = cta_threads;  // the caller knows better (a launch that runs BESIDE other kernels: 1024)
+  } else {
+    if ((long long)B * C > kNumSMs && smem <= 100 * 1024) threads = 512;
+    if ((long long)B * C > 2 * kNumSMs && smem <= 50 * 1024) threads = 256;
+  }
   if (const char* e = getenv("SPB_NMS_THREADS")) {
     const int t = atoi(e);
     if (t == 256 || t == 512 || t == 1024) threads = t;

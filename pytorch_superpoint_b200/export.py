@@ -175,7 +175,8 @@ class HAExporter:
                     _lib.check(L.spb_ha_finalize_batch(owned.data_ptr(), heat.data_ptr(), hi - lo, H, W,
                                                        side.cuda_stream), "ha_finalize")  # export.py:63
                 pts, counts, _ = ops.get_pts_from_heatmap_device(heat, self.conf_thresh, self.nms_dist,
-                                                                 self.border_remove, self.top_k, buf["cap"])
+                                                                 self.border_remove, self.top_k, buf["cap"],
+                                                                 background=True)  # beside the next batch's kernels
                 if self.subpixel_patch:  # model_wrap.py:200-234: all owned images in ONE launch, no host round trip
                     _lib.check(L.spb_soft_argmax_points_batch(heat.data_ptr(), hi - lo, H, W, pts.data_ptr(),
                                                               counts.data_ptr(), buf["cap"], self.subpixel_patch,

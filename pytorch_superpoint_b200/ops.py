@@ -212,8 +212,11 @@ def ha_finalize(sums):
     return heat
 
 
-def get_pts_from_heatmap_device(heat, conf_thresh, nms_dist, border_remove=4, top_k=0, capacity=None):
-    """Device-resident form: heat [B,H,W] cuda fp32 -> (pts [B,capacity,3] fp32, counts [B] i32, total [B] i32)."""
+def get_pts_from_heatmap_device(heat, conf_thresh, nms_dist, border_remove=4, top_k=0, capacity=None,
+                                background=False):
+    """Device-resident form: heat [B,H,W] cuda fp32 -> (pts [B,capacity,3] fp32, counts [B] i32, total [B] i32).
+    ``background``: the launch runs beside other kernels (a side stream under the next batch's convolutions): keep
+    the NMS kernel at one 1024-thread CTA per SM instead of the batch-dependent size."""
     assert heat.is_cuda and heat.dtype == torch.float32 and heat.dim() == 3
     heat = heat.contiguous()
     B, H, W = heat.shape
@@ -227,10 +230,10 @@ def get_pts_from_heatmap_device(heat, conf_thresh, nms_dist, border_remove=4, to
     nbytes = L.spb_nms_workspace_bytes(B, H, W, nms_dist)
     ws = torch.empty(nbytes, device=heat.device, dtype=torch.uint8)
     with torch.cuda.device(heat.device):
-        _lib.check(L.spb_get_pts_from_heatmap(heat.data_ptr(), B, H, W, float(conf_thresh), int(nms_dist),
-                                              int(border_remove), int(top_k or 0), capacity, pts.data_ptr(),
-                                              counts.data_ptr(), total.data_ptr(), ws.data_ptr(), nbytes, _stream()),
-                   "get_pts_from_heatmap")
+        _lib.check(L.spb_get_pts_from_heatmap_ex(heat.data_ptr(), B, H, W, float(conf_thresh), int(nms_dist),
+                                                 int(border_remove), int(top_k or 0), capacity, pts.data_ptr(),
+                                                 counts.data_ptr(), total.data_ptr(), ws.data_ptr(), nbytes,
+                                                 1024 if background else 0, _stream()), "get_pts_from_heatmap")
     return pts, counts, total
 
 
