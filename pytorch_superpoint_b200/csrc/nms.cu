@@ -292,39 +292,71 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) nms2_kernel(NmsParams
   cluster_barrier();
 
   while (true) {
-    // (A) row maxima for every local row / word some own undecided pixel looks at
-    for (int t = warp; t < nall; t += nwarp) {
-      const int lr = t / wpr, w = t % wpr, x = w * 32 + lane;
-      unsigned need = 0u;  // undecided bits of OWN rows within d rows of lr, this word
-      for (int q = max(lr - d, d); q <= min(lr + d, d + nr - 1); ++q) need |= und[q * ww + w + 1];
-      if (need == 0u) continue;
-      unsigned best = 0u, bj = 0u;
-      if (x < W) {
-        const unsigned bits = window_bits(und + lr * ww, x, d);
-        if (DT) {  // all taps issued at once (predicated loads), then the compare chain
-          unsigned k[2 * DT + 1];
+    // (A) row maxima for every local row / column some own undecided pixel looks at
+    if (DT == 4) {
+      // a warp takes 24 output columns of a row plus 4 columns on either side: every lane loads ITS masked key once
+      // and the leftmost maximum over [x-4, x+4] comes from four shuffle steps (windows of 2, 4, 8, 9 lanes)
+      for (int i = tid; i < nall; i += THREADS) {  // who looks at a row: undecided bits of the OWN rows within d
+        const int lr = i / wpr, w = i % wpr;
+        unsigned v = 0u;
+        for (int q = max(lr - d, d); q <= min(lr + d, d + nr - 1); ++q) v |= und[q * ww + w + 1];
+        hdil[lr * ww + w + 1] = v;  // (hdil is free until (C))
+      }
+      __syncthreads();
+      constexpr int OUT = 32 - 2 * 4;
+      const int spr = (W + OUT - 1) / OUT;
+      for (int t = warp; t < lrows * spr; t += nwarp) {
+        const int lr = t / spr, s0 = (t % spr) * OUT;  // first output column of the strip
+        const int start = s0 - 4 + 32;                 // bit position of lane 0's column in the padded bitmap row
+        const int wi = start >> 5, sh = start & 31;
+        const unsigned* vrow = hdil + lr * ww;
+        const unsigned vneed = __funnelshift_r(vrow[wi], wi + 1 < ww ? vrow[wi + 1] : 0u, sh);
+        if (((vneed >> 4) & ((1u << OUT) - 1u)) == 0u) continue;  // nobody looks at these columns of this row
+        const unsigned* urow = und + lr * ww;
+        const unsigned ubits = __funnelshift_r(urow[wi], wi + 1 < ww ? urow[wi + 1] : 0u, sh);
+        unsigned k = ((ubits >> lane) & 1u) ? key_l(lr, s0 - 4 + lane) : 0u;
+        unsigned o = (unsigned)lane;
+        const unsigned k0 = k;
 #pragma unroll
-          for (int j = 0; j <= 2 * DT; ++j) k[j] = ((bits >> j) & 1u) ? key_l(lr, x - DT + j) : 0u;
-#pragma unroll
-          for (int j = 0; j <= 2 * DT; ++j)
-            if (k[j] > best) {  // strict: the leftmost of equal keys stays
-              best = k[j];
-              bj = (unsigned)j;
-            }
-        } else {
-          unsigned rest = bits;
+        for (int st = 1; st <= 4; st <<= 1) {  // strict compares: the LEFT operand (smaller columns) keeps equal keys
+          const unsigned k2 = __shfl_down_sync(0xffffffffu, k, st), o2 = __shfl_down_sync(0xffffffffu, o, st);
+          if (k2 > k) {
+            k = k2;
+            o = o2;
+          }
+        }
+        const unsigned k8 = __shfl_down_sync(0xffffffffu, k0, 8);
+        if (k8 > k) {
+          k = k8;
+          o = (unsigned)lane + 8u;
+        }
+        const int x = s0 + lane;  // lane i < 24 holds the result for the window [s0 + i - 4, s0 + i + 4]
+        if (lane < OUT && x < W) {
+          rk[lr * W + x] = k;
+          rj[lr * W + x] = (unsigned char)(o - (unsigned)lane);
+        }
+      }
+    } else {
+      for (int t = warp; t < nall; t += nwarp) {
+        const int lr = t / wpr, w = t % wpr, x = w * 32 + lane;
+        unsigned need = 0u;  // undecided bits of OWN rows within d rows of lr, this word
+        for (int q = max(lr - d, d); q <= min(lr + d, d + nr - 1); ++q) need |= und[q * ww + w + 1];
+        if (need == 0u) continue;
+        unsigned best = 0u, bj = 0u;
+        if (x < W) {
+          unsigned rest = window_bits(und + lr * ww, x, d);
           while (rest) {
             const int j = __ffs(rest) - 1;
             rest &= rest - 1;
             const unsigned kk = key_l(lr, x - d + j);
-            if (kk > best) {
+            if (kk > best) {  // strict: the leftmost of equal keys stays
               best = kk;
               bj = (unsigned)j;
             }
           }
+          rk[lr * W + x] = best;
+          rj[lr * W + x] = (unsigned char)bj;
         }
-        rk[lr * W + x] = best;
-        rj[lr * W + x] = (unsigned char)bj;
       }
     }
     __syncthreads();
@@ -339,19 +371,16 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) nms2_kernel(NmsParams
           unsigned best = 0u;
           int br = 0, bj = 0;
           if (DT) {
-            unsigned k[2 * DT + 1], jj[2 * DT + 1];
+            unsigned k[2 * DT + 1];
 #pragma unroll
-            for (int r = 0; r <= 2 * DT; ++r) {
-              k[r] = rk[(ly + r) * W + x];
-              jj[r] = rj[(ly + r) * W + x];
-            }
+            for (int r = 0; r <= 2 * DT; ++r) k[r] = rk[(ly + r) * W + x];
 #pragma unroll
             for (int r = 0; r <= 2 * DT; ++r)
               if (k[r] > best) {  // strict: the topmost of equal keys stays
                 best = k[r];
                 br = r;
-                bj = (int)jj[r];
               }
+            bj = br == DT ? (int)rj[(ly + DT) * W + x] : -1;  // (only the centre row can make this pixel the winner)
           } else {
             for (int r = 0; r <= 2 * d; ++r) {
               const unsigned kk = rk[(ly + r) * W + x];
