@@ -296,3 +296,31 @@ def test_ingest_resize_gray_equals_opencv(spb, Hs, Ws, H, W):
         assert np.array_equal(got.cpu().numpy(), O.ingest_resize_gray(img, H, W))
     with pytest.raises(ValueError):
         ops.ingest_resize_gray(img[..., :2], (H, W))
+
+
+@pytest.mark.parametrize("cta", [0, 256, 512, 1024])
+@pytest.mark.parametrize("B,H,W,dist", [(3, 120, 160, 4), (40, 48, 72, 4), (2, 96, 100, 2)])
+def test_get_pts_every_cta_size_is_bit_identical(spb, cta, B, H, W, dist):
+    """spb_get_pts_from_heatmap_ex: the CTA size of the NMS kernel (automatic, or chosen by the caller for a background
+    launch) never changes the result -- every image identical to the oracle, for the reference's distance (separable
+    window maxima by warp shuffles) and another one (generic path)."""
+    from pytorch_superpoint_b200 import _lib
+    L = _lib.lib()
+    rng = np.random.RandomState(B + H + dist)
+    heat = (rng.rand(B, H, W) * 0.04).astype(np.float32)
+    heat[:, ::7, ::5] = np.round(heat[:, ::7, ::5] * 200) / 200          # some exact ties
+    h = torch.from_numpy(heat).cuda()
+    cap = -(-H // (dist + 1)) * -(-W // (dist + 1))
+    pts = torch.zeros((B, cap, 3), device="cuda")
+    cnt = torch.zeros((B,), dtype=torch.int32, device="cuda")
+    n = L.spb_nms_workspace_bytes(B, H, W, dist)
+    ws = torch.empty(n, dtype=torch.uint8, device="cuda")
+    _lib.check(L.spb_get_pts_from_heatmap_ex(h.data_ptr(), B, H, W, 0.015, dist, 4, 0, cap, pts.data_ptr(), cnt.data_ptr(),
+                                             None, ws.data_ptr(), n, cta, torch.cuda.current_stream().cuda_stream), "nms")
+    for b in range(B):
+        ref = O.get_pts_from_heatmap(heat[b], 0.015, dist, 4)
+        k = int(cnt[b])
+        assert k == ref.shape[1] and np.array_equal(pts[b, :k].cpu().numpy().astype(np.float64), ref.T)
+    if cta == 0:
+        assert L.spb_get_pts_from_heatmap_ex(h.data_ptr(), B, H, W, 0.015, dist, 4, 0, cap, pts.data_ptr(), cnt.data_ptr(),
+                                             None, ws.data_ptr(), n, 300, None) != 0   # not a CTA size
